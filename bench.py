@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- RK4 geodesic steps/s and frames/s of the render path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the one the headline metric is quoted on): ONE 3840x2160 frame, Kerr-like
+spin a=0.99, accretion disk + dust clouds with Doppler/redshift transfer, reference default camera
+(0,10,-60) yaw 0 pitch -10 (src/main.cpp:128-130), time 1.0, reference default CameraEffects, procedural
+4096x2048 RGBA8 skybox.  A "step" is one such frame.  At N>1 the frame is cut into cyclic 8-row bands, one
+set per rank (no communication while tracing), gathered to rank 0 over NCCL/NVLink and assembled there:
+total work is fixed, so scaling is "strong".
+
+The one JSON line printed by rank 0 follows the driver contract; see DESIGN.md "Measurement" for how
+`roofline`, `cpu_baseline`, `e2e` and `gpu_launches` are defined for this path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W4K, H4K = 3840, 2160
+CAM_POS, CAM_YAW, CAM_PITCH = (0.0, 10.0, -60.0), 0.0, -10.0
+SPIN = 0.99
+TIME = 1.0
+BAND_GROUP = 8
+FLOP_PER_STEP = 218.0          # algorithmic FLOP of one RK4 geodesic step, a != 0
+FP32_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4, at clocks.max.sm
+CPU_SAMPLE = (640, 360)        # bounded CPU sample of the same camera / parameters
+WORKLOAD = "3840x2160 Kerr a=0.99 volumetric (disk+dust) frame, camera C0, cyclic 8-row bands over N GPUs"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(w, h, repeats=1):
+    """The reference's own CPU implementation of the path (oracle/_ref when it was built, else the port),
+    all host threads, on a w x h sample of the bench camera/parameters.  Returns (steps, best_seconds, meta)."""
+    from oracle import Oracle, available
+    import relativisticraytracer_b200 as rrt
+    kind = "reference" if available("reference") else "port"
+    ora = Oracle(kind, auto_build=(kind == "port"))
+    prm = ora.default_params(spin_a=SPIN)
+    cam = ora.camera_from(CAM_POS, CAM_YAW, CAM_PITCH)
+    fx = ora.default_effects()
+    sky = rrt.procedural_sky(4096, 2048)
+    best, steps = 1e30, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        f = ora.render(prm, cam, fx, sky, TIME, w, h)
+        best = min(best, time.perf_counter() - t0)
+        steps = f.counters["rk4_steps"]
+    return steps, best, {"kind": kind, "cores": ora.num_threads(),
+                         "sample": f"{w}x{h} frame of the bench camera/params (a=0.99 disk+dust), "
+                                   f"g++ -O2 -ffp-contract=off, OpenMP dynamic rows"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, h = CPU_SAMPLE
+    for _ in range(args.warmup):
+        cpu_reference_run(w, h)
+    tot_t, steps = 0.0, 0
+    for _ in range(args.steps):
+        steps, dt, meta = cpu_reference_run(w, h)
+        tot_t += dt
+    per = tot_t / max(args.steps, 1)
+    value = steps / per
+    line = {
+        "impl": "reference", "metric": "geodesic_rk4_steps_per_s", "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": meta["sample"]},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": meta["cores"], "kind": meta["kind"],
+                         "sample": meta["sample"]},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s_4k_equiv": value / (steps / (w * h)) / (W4K * H4K),
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import relativisticraytracer_b200 as rrt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.cuda.current_device()
+    w, h = args.width, args.height
+
+    r = rrt.Renderer(dev)
+    sky = r.create_sky(rrt.procedural_sky(4096, 2048))
+    prm = rrt.default_params(spin_a=SPIN)
+    cam = rrt.camera_state_from(CAM_POS, CAM_YAW, CAM_PITCH)
+    fx = rrt.default_effects()
+    band = rrt.Band(rank, world, BAND_GROUP)
+    rows_mine = r.band_rows(band, h)
+    rows_max = max(r.band_rows(rrt.Band(i, world, BAND_GROUP), h) for i in range(world))
+    packed = torch.zeros((rows_max, w, 4), dtype=torch.uint8, device="cuda")
+    gathered = torch.zeros((world, rows_max, w, 4), dtype=torch.uint8, device="cuda") if (world > 1 and rank == 0) else None
+    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    host_frame = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def one_frame(to_host: bool):
+        """the hot path for one step; returns number of OUR kernels launched"""
+        if world == 1:
+            if to_host:
+                r.render_host(prm, cam, fx, sky, TIME, w, h, host_frame)        # C-ABI call, host destination
+            else:
+                r.render(prm, cam, fx, sky, TIME, w, h, out=frame, layout=rrt.OUT_FRAME)
+            return 1
+        r.render(prm, cam, fx, sky, TIME, w, h, band=band, out=packed, layout=rrt.OUT_PACKED)
+        dist.gather(packed, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+        n = 1
+        if rank == 0:
+            r.assemble_bands(gathered, rows_max, w, h, world, BAND_GROUP, frame=frame)
+            n += 1
+            if to_host:
+                host_frame.copy_(frame, non_blocking=True)
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps: int, to_host: bool):
+        """sum of per-step device times (CUDA events on the launching stream), L2 flushed between steps"""
+        total_ms, kernel_ms, launches = 0.0, 0.0, 0
+        for _ in range(n_steps):
+            flush.fill_(1)
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            t0 = time.perf_counter()
+            e0.record(stream)
+            if world == 1 and to_host:
+                launches += one_frame(True)      # synchronous inside (D2H), host clock is the honest one
+                torch.cuda.synchronize()
+                total_ms += (time.perf_counter() - t0) * 1e3
+                continue
+            if world == 1:
+                launches += one_frame(False)
+                e1.record(stream)
+                e2.record(stream)
+            else:
+                r.render(prm, cam, fx, sky, TIME, w, h, band=band, out=packed, layout=rrt.OUT_PACKED)
+                e1.record(stream)
+                dist.gather(packed, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+                launches += 1
+                if rank == 0:
+                    r.assemble_bands(gathered, rows_max, w, h, world, BAND_GROUP, frame=frame)
+                    launches += 1
+                    if to_host:
+                        host_frame.copy_(frame, non_blocking=True)
+                e2.record(stream)
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e2)
+            kernel_ms += e0.elapsed_time(e1)
+        return total_ms, kernel_ms, launches
+
+    # ---- warm-up, then the counted work of one step -------------------------------------------------
+    timed(args.warmup, False)
+    r.read_counters(reset=True)
+    one_frame(False)
+    torch.cuda.synchronize()
+    cnt = r.read_counters(reset=True)
+    steps_local = torch.tensor([cnt["rk4_steps"], cnt["disk_evals"], cnt["dust_evals"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(steps_local)
+    rk4_per_frame, disk_evals, dust_evals = (float(x) for x in steps_local.tolist())
+
+    # ---- timed region: device-resident ---------------------------------------------------------------
+    with ClockSampler(dev) as clk:
+        barrier()
+        tot_ms, kern_ms, launches = timed(args.steps, False)
+        barrier()
+    # ---- timed region: end to end (host destination) ---------------------------------------------------
+    timed(1, True)
+    e2e_ms, _, _ = timed(args.steps, True)
+
+    t = torch.tensor([tot_ms, kern_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms, kern_ms, e2e_ms = (float(x) for x in t.tolist())
+    ms_per_step = tot_ms / args.steps
+    kern_ms_per_step = kern_ms / args.steps
+    e2e_ms_per_step = e2e_ms / args.steps
+    value = rk4_per_frame / (ms_per_step * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (render_kernel): FP32 FMA pipe -------------------------------
+    fp32_meas, _ = r.fp32_peak(4096)
+    kern_steps_per_s = (rk4_per_frame / world) / (kern_ms_per_step * 1e-3)      # this rank's kernel (max over ranks time)
+    achieved_tflops = FLOP_PER_STEP * kern_steps_per_s / 1e12
+    roofline = {
+        "bound": "fp32_fma", "achieved": achieved_tflops, "peak": fp32_meas, "unit": "TFLOP/s",
+        "frac": achieved_tflops / fp32_meas, "traffic": None,
+        "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
+        "peak_theoretical": FP32_THEORETICAL_TFLOPS, "frac_of_theoretical": achieved_tflops / FP32_THEORETICAL_TFLOPS,
+        "flop_per_step": FLOP_PER_STEP, "kernel": "render_kernel<spin,media>", "kernel_ms": kern_ms_per_step,
+        "note": "geodesic-step FLOPs only; disk/dust density evaluations (1.1k/4.1k FLOP each) are not credited",
+    }
+
+    line = {
+        "metric": "geodesic_rk4_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD if (w, h) == (W4K, H4K) else f"{w}x{h} variant of: {WORKLOAD}",
+                   "width": w, "height": h, "spin_a": SPIN, "media": "disk+dust", "camera": "C0", "band_group_rows": BAND_GROUP,
+                   "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) between timed steps",
+                   "rk4_steps_per_frame": rk4_per_frame, "disk_evals_per_frame": disk_evals, "dust_evals_per_frame": dust_evals},
+        "frames_per_s": 1e3 / ms_per_step,
+        "roofline": roofline,
+        "e2e": {"value": rk4_per_frame / (e2e_ms_per_step * 1e-3), "unit": "steps/s",
+                "frames_per_s": 1e3 / e2e_ms_per_step, "ms_per_step": e2e_ms_per_step,
+                "h2d_bytes_per_step": 64 + 48 + 36 + 16, "d2h_bytes_per_step": w * h * 4,
+                "path": "rrt_render_host (C ABI, pinned host frame)" if world == 1 else "rrt_render per rank + NCCL gather + rrt_assemble_bands + D2H"},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        cw, ch = CPU_SAMPLE
+        steps_c, secs, meta = cpu_reference_run(cw, ch)
+        line["cpu_baseline"] = {"value": steps_c / secs, "unit": "steps/s", "cores": meta["cores"], "kind": meta["kind"],
+                                "sample": meta["sample"], "seconds": secs}
+    if world == 1 and not args.no_ref_cuda:
+        try:
+            from oracle import RefCuda, Oracle
+            if RefCuda.available():
+                oc = Oracle("port")
+                _, best, mean = RefCuda().render(SPIN, oc.camera_from(CAM_POS, CAM_YAW, CAM_PITCH), oc.default_effects(),
+                                                 rrt.procedural_sky(4096, 2048), TIME, w, h, reps=3)
+                line["ref_cuda_baseline"] = {"what": "reference src/raymarcher.cu unmodified, nvcc -O3 sm_100a, same frame",
+                                             "ms_per_frame": mean, "best_ms": best, "steps_per_s": rk4_per_frame / (mean * 1e-3)}
+        except Exception as e:  # a baseline, never the product: report and move on
+            line["ref_cuda_baseline"] = {"unavailable": str(e)[:200]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+/*
+ * rrt.h -- C ABI of the B200-native render path (librrt_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of levi2234/RelativisticRayTracer: the per-pixel
+ * geodesic integration + volumetric disk/dust march + skybox lookup that the reference runs in
+ * raymarch_kernel (src/raymarcher.cu:15-174) behind launch_raymarch (include/raymarcher.h:19,
+ * src/raymarcher.cu:176-180; sole caller renderFrame, src/main.cpp:467).
+ *
+ * Plain C: POD structs, raw pointers and sizes, int error codes.  No torch, no C++ types.
+ * The C++ shim with the reference's exact launch_raymarch signature sits on top of this file in
+ * include/compat/raymarcher.h + csrc/rrt_compat.cu.
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device of compute capability
+ * 10.0 and fails with RRT_ERR_NO_DEVICE / RRT_ERR_CUDA otherwise.
+ */
+#ifndef RRT_H
+#define RRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRT_ABI_VERSION 1
+
+/* ---- error codes -------------------------------------------------------------------------------- */
+#define RRT_OK 0
+#define RRT_ERR_BAD_ARG (-1)   /* NULL pointer, non-positive size, bad band, ... */
+#define RRT_ERR_CUDA (-2)      /* a CUDA runtime call or the kernel failed; see rrt_last_error() */
+#define RRT_ERR_NO_DEVICE (-3) /* no usable sm_100 device */
+#define RRT_ERR_NOMEM (-4)
+
+/* ---- parameter surface ---------------------------------------------------------------------------
+ * The reference bakes these in as macros (include/config.h); here they are run-time fields with the
+ * same names in lower case, defaults = the reference's values (rrt_default_params). */
+typedef struct rrt_params {
+    float spin_a;           /* SPIN_A            config.h:21  (reference ships 0.0f) */
+    float event_horizon;    /* EVENT_HORIZON     config.h:29 */
+    float isco_radius;      /* ISCO_RADIUS       config.h:33 */
+    float disk_out;         /* DISK_OUT_M        config.h:34 */
+    float disk_h;           /* DISK_H_M          config.h:35 */
+    float disk_luminosity;  /* DISK_LUMINOSITY   config.h:36 */
+    float disk_opacity;     /* DISK_OPACITY      config.h:37 */
+    float exposure;         /* EXPOSURE          config.h:38 */
+    float cloud_h;          /* CLOUD_H_M         config.h:41 */
+    float cloud_out;        /* CLOUD_OUT_M       config.h:42 */
+    float cloud_opacity;    /* CLOUD_OPACITY     config.h:43 */
+    float cloud_luminosity; /* CLOUD_LUMINOSITY  config.h:44 */
+    float step_size;        /* STEP_SIZE_M       config.h:47 */
+    float disk_temp_ref;    /* DISK_TEMP_REF     config.h:18 */
+    int32_t max_steps;      /* MAX_STEPS         config.h:48 */
+    uint32_t flags;         /* RRT_FLAG_* */
+} rrt_params;
+
+#define RRT_FLAG_DISK 1u /* accretion-disk medium  (getAccretionDensity, raymarcher.cu:68) */
+#define RRT_FLAG_DUST 2u /* dust-cloud medium      (getDustCloudDensity, raymarcher.cu:69) */
+
+/* struct CameraState, include/raymarcher.h:11-16: four packed float3, 48 bytes. */
+typedef struct rrt_camera {
+    float pos[3], forward[3], right[3], up[3];
+} rrt_camera;
+
+/* struct CameraEffects, include/camera_effects/camera_settings.h:4-17, as plain C (bool -> int32). */
+typedef struct rrt_effects {
+    int32_t use_bloom;
+    float bloom_threshold, bloom_intensity;
+    int32_t use_vignette;
+    float vignette_intensity;
+    int32_t use_ca;
+    float ca_amount;
+    int32_t use_lens;
+    float distortion_amount;
+} rrt_effects;
+
+/* Row-band ownership for multi-GPU frames: image rows are cut into groups of `group` consecutive
+ * rows and group k belongs to rank (k % nranks).  NULL / {0,1,1} = the whole frame. */
+typedef struct rrt_band {
+    int32_t rank, nranks, group;
+} rrt_band;
+
+/* Optional per-pixel DEVICE planes for parity checking, indexed [y*w + x] (not row-flipped).
+ * Any pointer may be NULL.  float planes are float4 per pixel (16-byte aligned, coalesced). */
+typedef struct rrt_planes {
+    float* hdr;     /* final_hdr.rgb before camera effects (raymarcher.cu:148-150), w = transmittance */
+    float* dir;     /* normalize(vel) at exit (raymarcher.cu:129); zeros for captured rays */
+    float* emis;    /* accumulated emission I.rgb (raymarcher.cu:111-113) */
+    float* pos;     /* final position */
+    float* vel;     /* final (un-normalised) velocity */
+    uint8_t* cls;   /* RRT_CLS_* | RRT_CLSF_* */
+    int32_t* steps; /* RK4 steps taken */
+} rrt_planes;
+
+#define RRT_CLS_CAPTURED 0u /* r < 1.01*EVENT_HORIZON (raymarcher.cu:47-51) */
+#define RRT_CLS_DISK_HIT 1u /* not captured and >= 1 sample passed the 0.001 density gate (raymarcher.cu:71) */
+#define RRT_CLS_ESCAPED 2u  /* not captured, no medium touched */
+#define RRT_CLS_MASK 3u
+#define RRT_CLSF_EXHAUSTED 4u /* ran MAX_STEPS iterations (raymarcher.cu:41) */
+#define RRT_CLSF_TOUCHED 8u
+
+typedef struct rrt_counters {
+    uint64_t rk4_steps;     /* integrate_rk4 calls -- the unit of the headline metric */
+    uint64_t disk_evals;    /* disk-density evaluations */
+    uint64_t dust_evals;    /* dust-density evaluations */
+    uint64_t dense_samples; /* samples past the 0.001 gate */
+    uint64_t n_captured, n_escaped, n_exhausted, n_touched;
+} rrt_counters;
+
+/* where the uchar4 pixels go */
+#define RRT_OUT_FRAME 0  /* d_out is the full w*h frame; pixel (x,y) -> [(h-1-y)*w + x] as raymarcher.cu:168 */
+#define RRT_OUT_PACKED 1 /* d_out holds only this band's rows, local row l -> [l*w + x], not flipped */
+
+typedef struct rrt_context rrt_context; /* per-device scratch: counters, staging, default stream */
+typedef struct rrt_sky rrt_sky;         /* cudaArray + texture object */
+
+/* ---- lifetime ----------------------------------------------------------------------------------- */
+int rrt_abi_version(void);
+const char* rrt_build_info(void);                      /* arch + flags the library was compiled with */
+int rrt_context_create(int device, rrt_context** out); /* device = CUDA ordinal */
+void rrt_context_destroy(rrt_context* ctx);
+const char* rrt_last_error(const rrt_context* ctx);    /* ctx may be NULL: last create failure */
+
+void rrt_default_params(rrt_params* out);   /* the values of include/config.h */
+void rrt_default_effects(rrt_effects* out); /* the default member initialisers of CameraEffects */
+
+/* ---- skybox: replaces loadSkybox's device half, src/main.cpp:246-263 ----------------------------- */
+/* RGBA8 rows top-down, exactly what stbi_load(...,4) returns; builds a cudaArray and a texture object
+ * with addressMode {Wrap, Clamp}, linear filter, normalised-float read, normalised coordinates. */
+int rrt_sky_create(rrt_context* ctx, const uint8_t* host_rgba, int w, int h, rrt_sky** out);
+uint64_t rrt_sky_texture(const rrt_sky* sky); /* the cudaTextureObject_t, usable with launch_raymarch */
+void rrt_sky_destroy(rrt_sky* sky);
+
+/* ---- the hot path: replaces launch_raymarch / raymarch_kernel ------------------------------------ */
+/* Asynchronous on `stream` (a cudaStream_t; NULL = the legacy default stream, like the reference).
+ * d_out: device uchar4 buffer (layout per out_layout).  planes: NULL or device planes.
+ * RK4-step and class counters accumulate in the context until rrt_read_counters resets them. */
+int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
+               uint64_t sky_texture, float time, int w, int h, const rrt_band* band, void* d_out, int out_layout,
+               const rrt_planes* planes, void* stream);
+
+/* Same call with a HOST destination: renders into a context-owned device frame, copies it to
+ * host_rgba (w*h*4 bytes, reference layout) and synchronises.  This is the end-to-end entry point. */
+int rrt_render_host(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
+                    uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba);
+
+/* Number of rows a band owns in an h-row image (packed buffer height). */
+int rrt_band_rows(const rrt_band* band, int h);
+
+/* Scatter nranks packed band buffers (rank-major, each `rows_per_rank` rows of w uchar4) into the full
+ * row-flipped frame -- the step after the NVLink gather on the encoding GPU. */
+int rrt_assemble_bands(rrt_context* ctx, const void* d_packed, int rows_per_rank, int w, int h, int nranks,
+                       int group, void* d_frame, void* stream);
+
+/* Synchronises the context's work, copies the counters out and optionally zeroes them. */
+int rrt_read_counters(rrt_context* ctx, rrt_counters* out, int reset);
+
+/* ---- function-level probes (HOST arrays in, HOST arrays out; float3 packed xyz) -------------------
+ * Device implementations of the interfaces north_star names, callable one function at a time so each
+ * can be checked against the oracle:
+ *   getGeodesicAcc          geodesics.h:30-45        integrate_rk4   integrators.h:23-59
+ *   calculateRedshiftFactor geodesics.h:11-25        integrate_euler integrators.h:12-18
+ *   hash31/noise3D/fbm      math_utils.h:91-121      getDiskTemperature / getAccretionDensity /
+ *   tex2D<float4>           raymarcher.cu:139        getDustCloudDensity  densities.h:12-132 */
+int rrt_geodesic_acc_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, const float* v, float* out);
+int rrt_rk4_step_batch(rrt_context* ctx, const rrt_params* prm, int n, float* p, float* v, const float* h);
+int rrt_euler_step_batch(rrt_context* ctx, const rrt_params* prm, int n, float* p, float* v, const float* h);
+int rrt_redshift_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, const float* v, float* out);
+int rrt_hash31_batch(rrt_context* ctx, int n, const float* p, float* out);
+int rrt_noise3d_batch(rrt_context* ctx, int n, const float* p, float* out);
+int rrt_fbm_batch(rrt_context* ctx, int n, const float* p, int octaves, float* out);
+int rrt_disk_temperature_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* r, float* out);
+int rrt_disk_density_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, float time, float* out);
+int rrt_dust_density_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, float time, float* out);
+int rrt_sky_sample_batch(rrt_context* ctx, uint64_t sky_texture, int n, const float* tx, const float* ty, float* out4);
+
+/* ---- host camera + keyframe paths: the step before the hot path ---------------------------------------
+ * Pure host code (no device needed).  rrt_camera_from replaces CameraController::getCUDAStateFrom
+ * (src/main.cpp:141-167; angles in degrees, the reference's 3.14159f and float sinf/cosf).
+ * rrt_path_state replaces PathController::getInterpolatedState (src/main.cpp:176-203) over the three
+ * built-in keyframe tables of initDefaultPaths (src/camera_paths.cpp:31-73) with catmull_rom (:6-22) and
+ * lerp_angle (:25-29).  rrt_path_clock reproduces the recorder's fixed clock: pathTime after `frame`
+ * float accumulations of 1.0f/fps (src/main.cpp:511-516, 210-212). */
+void rrt_camera_from(const float pos[3], float yaw_deg, float pitch_deg, rrt_camera* out);
+int rrt_path_count(void);
+const char* rrt_path_name(int path_index);
+int rrt_path_num_keys(int path_index);
+float rrt_path_duration(int path_index);
+int rrt_path_state(int path_index, float t, rrt_camera* out, float pos_yaw_pitch[5]);
+float rrt_path_clock(int frame, float fps);
+
+/* ---- measurement helper ---------------------------------------------------------------------------
+ * Register-resident FFMA-chain microbenchmark: the FP32 roofline denominator MEASURED_PEAKS.json lacks.
+ * Returns achieved FP32 TFLOP/s (2 flop per FFMA) over `iters` dependent-chain iterations. */
+int rrt_fp32_peak_probe(rrt_context* ctx, int iters, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRT_H */

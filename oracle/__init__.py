@@ -268,3 +268,36 @@ class Oracle:
         out = np.empty((len(tx), 4), np.float32)
         self._fn("tex2d")(_ptr(sky), sky.shape[1], sky.shape[0], len(tx), _ptr(tx), _ptr(ty), _ptr(out))
         return out
+
+
+class RefCuda:
+    """The reference's own CUDA raymarcher (src/raymarcher.cu, unmodified, nvcc defaults + sm_100a) behind a
+    headless harness (oracle/ref_cuda_harness.cu).  Needs a GPU.  spin must be 0.0 or 0.99 (compile-time there)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libref_cuda.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.refcuda_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.refcuda_render.restype = C.c_int
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_cuda.so"))
+
+    def render(self, spin: float, cam, fx, sky: np.ndarray, time: float, w: int, h: int, reps: int = 1):
+        assert spin in (0.0, 0.99)
+        sky = np.ascontiguousarray(sky, dtype=np.uint8)
+        cam12 = np.frombuffer(bytes(cam), dtype=np.float32).copy()
+        fx_i = np.array([fx.use_bloom, fx.use_vignette, fx.use_ca, fx.use_lens], np.int32)
+        fx_f = np.array([fx.bloom_threshold, fx.bloom_intensity, fx.vignette_intensity, fx.ca_amount,
+                         fx.distortion_amount], np.float32)
+        out = np.zeros((h, w, 4), np.uint8)
+        best, mean = C.c_float(), C.c_float()
+        rc = self.lib.refcuda_render(1 if spin != 0.0 else 0, w, h, float(time), _ptr(cam12), _ptr(fx_i), _ptr(fx_f),
+                                     _ptr(sky), sky.shape[1], sky.shape[0], _ptr(out), int(reps), C.byref(best), C.byref(mean))
+        if rc != 0:
+            raise RuntimeError(f"refcuda_render rc={rc}")
+        return out, float(best.value), float(mean.value)

@@ -1,0 +1,819 @@
+// rrt_b200.cu -- render kernels, probe kernels and the C ABI (include/rrt.h) of librrt_b200.so.
+//
+// Replaces, for the hot path only, raymarch_kernel + launch_raymarch (reference src/raymarcher.cu:15-180).
+// Compile for sm_100a with -fmad=false (see the rounding contract in rrt_device.cuh).
+//
+// Kernel organisation (B200: 148 SMs, no tensor-core work on this path -- it is FP32 FMA-pipe bound):
+//   * persistent warps: grid = SMs x resident CTAs; each warp pulls 8x4-pixel tiles from a global
+//     atomic ticket until the frame is exhausted, so SMs never idle behind a slow tile;
+//   * ray state (p, v, I, T, counters) lives in registers for the whole ray -- nothing is staged in HBM;
+//   * camera, effects and every derived constant arrive in the kernel parameter block, i.e. the
+//     constant bank, and are read as free FFMA/FMUL operands;
+//   * the skybox is a texture object (wrap-x / clamp-y / linear), 33.5 MB, L2-resident;
+//   * outputs: 4 B/pixel uchar4 (row-flipped like the reference) plus optional float4 parity planes.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/rrt.h"
+#include "rrt_device.cuh"
+
+using rrt::Consts;
+using rrt::V3;
+using rrt::mk;
+
+namespace {
+
+struct FrameArgs {
+    Consts C;
+    rrt_camera cam;
+    rrt_effects fx;
+    float time;
+    int w, h;
+    int band_rank, band_nranks, band_group, local_rows;
+    int out_layout;
+    uchar4* out;
+    rrt_planes planes;
+    cudaTextureObject_t sky;
+    unsigned long long* counters;  // rrt_counters, 8 x u64
+    unsigned int* ticket;          // tile ticket for this launch
+};
+
+constexpr int kTileW = 8, kTileH = 4;  // one warp = 8x4 pixels
+constexpr int kBlock = 128;
+
+struct RayResult {
+    float hdr[3], T, I[3];
+    V3 d, p, v;
+    float uvx, uvy;
+    int steps;
+    unsigned n_disk, n_dust, n_dense;
+    bool captured, touched, exhausted;
+};
+
+// One ray: reference raymarch_kernel lines 20-150.
+template <bool SPIN, bool MEDIA>
+__device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayResult& R) {
+    const Consts& C = A.C;
+    float uvx = (float)x / (float)A.w, uvy = (float)y / (float)A.h;  // :20
+    if (A.fx.use_lens) {                                              // :23-25, post_processing.h:19-24
+        float tu = uvx - 0.5f, tv = uvy - 0.5f;
+        float rr = tu * tu + tv * tv;
+        float f = 1.0f + rr * A.fx.distortion_amount;
+        uvx = tu * f + 0.5f;
+        uvy = tv * f + 0.5f;
+    }
+    float uc = uvx * 2.0f - 1.0f;  // :27
+    float vc = uvy * 2.0f - 1.0f;  // :28
+    float aspect = (float)A.w / (float)A.h;
+    uc *= aspect;  // :30
+    V3 p = mk(A.cam.pos[0], A.cam.pos[1], A.cam.pos[2]);
+    V3 v = rrt::unit3(mk(A.cam.forward[0] + (A.cam.right[0] * uc + A.cam.up[0] * vc),
+                         A.cam.forward[1] + (A.cam.right[1] * uc + A.cam.up[1] * vc),
+                         A.cam.forward[2] + (A.cam.right[2] * uc + A.cam.up[2] * vc)));  // :33-34
+
+    float Ir = 0.f, Ig = 0.f, Ib = 0.f, T = 1.0f;
+    bool captured = false, touched = false, escaped = false;
+    int it = 0;
+    unsigned n_disk = 0, n_dust = 0, n_dense = 0;
+    const int max_steps = C.max_steps;
+    const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
+#pragma unroll 1
+    for (; it < max_steps; ++it) {                                                        // :41
+        const float r2 = rrt::dot3(p, p);
+        const float r = sqrtf(r2);                                                        // :44
+        if (r < C.horizon_r) { captured = true; T = 0.0f; break; }                        // :47-51
+        const bool near_bh = r < 18.0f;                                                   // :56
+        const bool disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;           // :57
+        const bool dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;           // :58
+        const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));               // :60-62
+        const float h = C.h[zi];
+        const V3 q = p;  // pre-step position: media and the escape test use it (:68-69, :120)
+        rrt::rk4_step<SPIN>(C, p, v, h, C.hh[zi], C.h6[zi], r2, r);                       // :64
+        if (MEDIA && (disk_zone || dust_zone)) {                                          // :67
+            float dd = 0.0f, dc = 0.0f;
+            if (disk_zone && want_disk) { dd = rrt::disk_density(C, q, A.time); ++n_disk; }
+            if (dust_zone && want_dust) { dc = rrt::dust_density(C, q, A.time); ++n_dust; }
+            if (dd > 0.001f || dc > 0.001f) {                                             // :71
+                touched = true;
+                ++n_dense;
+                float er = 0.f, eg = 0.f, eb = 0.f, kappa = 0.f;
+                const float g = rrt::redshift(C, q, v);  // same arguments in both branches (:77, :92)
+                if (dd > 0.001f) {                                                        // :76-88
+                    float Tk = rrt::disk_temperature(C, r);
+                    float tn = powf(Tk / C.disk_temp_ref, 0.5f);
+                    float bol = powf(g, 4.0f) * tn * dd * C.disk_luminosity;
+                    float ct = g * powf(Tk / C.disk_temp_ref, 0.4f) * 2.5f;
+                    er += 1.0f * bol;
+                    eg += fminf(0.25f, 0.12f * ct) * bol;
+                    eb += fmaxf(0.0f, 0.01f * (ct - 2.0f)) * bol;
+                    kappa += dd * C.disk_opacity;
+                }
+                if (dc > 0.001f) {                                                        // :91-105
+                    float light = 0.5f + 3.0f * powf(C.isco / fmaxf(r, C.isco), 1.2f);
+                    float J = dc * C.cloud_luminosity * light;
+                    float sh = rrt::sstep(0.7f, 1.3f, g);
+                    er += 0.60f * J * rrt::mixf(1.2f, 0.8f, sh);
+                    eg += 0.65f * J * rrt::mixf(0.8f, 1.1f, sh);
+                    eb += 0.80f * J * rrt::mixf(0.6f, 1.4f, sh);
+                    kappa += dc * C.cloud_opacity;
+                }
+                float tau = kappa * h;                                                    // :107
+                float s = expf(-tau);
+                float wgt = (1.0f - s) * T;
+                Ir += er * wgt; Ig += eg * wgt; Ib += eb * wgt;                           // :111-113
+                T *= s;                                                                   // :115
+            }
+        }
+        if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { escaped = true; ++it; break; }       // :120 (this step counted)
+    }
+    // `it` counts executed integrate_rk4 calls on every exit path
+    R.exhausted = !captured && !escaped;  // the for loop ran out (:41)
+    R.steps = it;
+    R.captured = captured;
+    R.touched = touched;
+    R.n_disk = n_disk; R.n_dust = n_dust; R.n_dense = n_dense;
+    R.p = p; R.v = v; R.T = T;
+    R.I[0] = Ir; R.I[1] = Ig; R.I[2] = Ib;
+    R.uvx = uvx; R.uvy = uvy;
+}
+
+template <bool SPIN, bool MEDIA>
+__global__ void __launch_bounds__(kBlock) render_kernel(const __grid_constant__ FrameArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int ntx = (A.w + kTileW - 1) / kTileW;
+    const int nty = (A.local_rows + kTileH - 1) / kTileH;
+    const unsigned ntiles = (unsigned)(ntx * nty);
+    unsigned long long c_steps = 0, c_disk = 0, c_dust = 0, c_dense = 0;
+    unsigned c_cap = 0, c_esc = 0, c_exh = 0, c_touch = 0;
+
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(A.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        const int tx = (int)(tile % (unsigned)ntx), ty = (int)(tile / (unsigned)ntx);
+        const int x = tx * kTileW + (lane & (kTileW - 1));
+        const int ly = ty * kTileH + (lane >> 3);
+        if (x >= A.w || ly >= A.local_rows) continue;
+        const int grp = ly / A.band_group;
+        const int y = (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
+        if (y >= A.h) continue;
+
+        RayResult R;
+        trace_ray<SPIN, MEDIA>(A, x, y, R);
+
+        // ---- background + final assembly, reference :127-173 ----
+        float bg[3] = {0.f, 0.f, 0.f};
+        V3 d = mk(0.f, 0.f, 0.f);
+        if (!R.captured) {
+            d = rrt::unit3(R.v);
+            const float off = A.fx.use_ca ? A.fx.ca_amount : 0.0f;
+            const float theta = asinf(d.y);
+            const float ty_ = 0.5f - theta / rrt::kPi;
+            const float phi0 = atan2f(d.z, d.x);
+            float4 sR = tex2D<float4>(A.sky, 0.5f + (phi0 + off) / (2.0f * rrt::kPi), ty_);
+            float4 sG = tex2D<float4>(A.sky, 0.5f + (phi0 + 0.0f) / (2.0f * rrt::kPi), ty_);
+            float4 sB = tex2D<float4>(A.sky, 0.5f + (phi0 + -off) / (2.0f * rrt::kPi), ty_);
+            bg[0] = sR.x; bg[1] = sG.y; bg[2] = sB.z;
+        }
+        float hr = R.I[0] + bg[0] * R.T, hg = R.I[1] + bg[1] * R.T, hb = R.I[2] + bg[2] * R.T;  // :148-150
+
+        const size_t pix = (size_t)y * A.w + x;
+        uint8_t cls = (uint8_t)((R.captured ? RRT_CLS_CAPTURED : (R.touched ? RRT_CLS_DISK_HIT : RRT_CLS_ESCAPED)) |
+                                (R.exhausted ? RRT_CLSF_EXHAUSTED : 0u) | (R.touched ? RRT_CLSF_TOUCHED : 0u));
+        if (A.planes.hdr) reinterpret_cast<float4*>(A.planes.hdr)[pix] = make_float4(hr, hg, hb, R.T);
+        if (A.planes.dir) reinterpret_cast<float4*>(A.planes.dir)[pix] = make_float4(d.x, d.y, d.z, 0.f);
+        if (A.planes.emis) reinterpret_cast<float4*>(A.planes.emis)[pix] = make_float4(R.I[0], R.I[1], R.I[2], 0.f);
+        if (A.planes.pos) reinterpret_cast<float4*>(A.planes.pos)[pix] = make_float4(R.p.x, R.p.y, R.p.z, 0.f);
+        if (A.planes.vel) reinterpret_cast<float4*>(A.planes.vel)[pix] = make_float4(R.v.x, R.v.y, R.v.z, 0.f);
+        if (A.planes.cls) A.planes.cls[pix] = cls;
+        if (A.planes.steps) A.planes.steps[pix] = R.steps;
+
+        if (A.fx.use_bloom) {  // :154-157, post_processing.h:27-31
+            float lum = hr * 0.2126f + hg * 0.7152f + hb * 0.0722f;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            if (lum > A.fx.bloom_threshold) { b0 = hr; b1 = hg; b2 = hb; }
+            hr = hr + b0 * A.fx.bloom_intensity;
+            hg = hg + b1 * A.fx.bloom_intensity;
+            hb = hb + b2 * A.fx.bloom_intensity;
+        }
+        if (A.fx.use_vignette) {  // :159-161, post_processing.h:13-17
+            float dx = R.uvx - 0.5f, dy = R.uvy - 0.5f;
+            float dist = sqrtf(dx * dx + dy * dy + 0.0f);
+            float vg = rrt::sstep(0.8f, 0.2f, dist * A.fx.vignette_intensity);
+            hr *= vg; hg *= vg; hb *= vg;
+        }
+        float o_r = 1.0f - expf(-hr * A.C.exposure);  // :164-166
+        float o_g = 1.0f - expf(-hg * A.C.exposure);
+        float o_b = 1.0f - expf(-hb * A.C.exposure);
+        uchar4 px = make_uchar4((unsigned char)(o_r * 255), (unsigned char)(o_g * 255), (unsigned char)(o_b * 255), 255);
+        if (A.out) {
+            if (A.out_layout == RRT_OUT_FRAME) A.out[(size_t)(A.h - 1 - y) * A.w + x] = px;  // :168
+            else A.out[(size_t)ly * A.w + x] = px;
+        }
+        c_steps += (unsigned)R.steps;
+        c_disk += R.n_disk; c_dust += R.n_dust; c_dense += R.n_dense;
+        c_cap += R.captured; c_exh += R.exhausted; c_esc += (!R.captured && !R.exhausted); c_touch += R.touched;
+    }
+
+    // one set of atomics per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_steps += __shfl_xor_sync(0xffffffffu, c_steps, o);
+        c_disk += __shfl_xor_sync(0xffffffffu, c_disk, o);
+        c_dust += __shfl_xor_sync(0xffffffffu, c_dust, o);
+        c_dense += __shfl_xor_sync(0xffffffffu, c_dense, o);
+        c_cap += __shfl_xor_sync(0xffffffffu, c_cap, o);
+        c_esc += __shfl_xor_sync(0xffffffffu, c_esc, o);
+        c_exh += __shfl_xor_sync(0xffffffffu, c_exh, o);
+        c_touch += __shfl_xor_sync(0xffffffffu, c_touch, o);
+    }
+    if (lane == 0 && A.counters) {
+        atomicAdd(A.counters + 0, c_steps);
+        atomicAdd(A.counters + 1, c_disk);
+        atomicAdd(A.counters + 2, c_dust);
+        atomicAdd(A.counters + 3, c_dense);
+        atomicAdd(A.counters + 4, (unsigned long long)c_cap);
+        atomicAdd(A.counters + 5, (unsigned long long)c_esc);
+        atomicAdd(A.counters + 6, (unsigned long long)c_exh);
+        atomicAdd(A.counters + 7, (unsigned long long)c_touch);
+    }
+}
+
+// ---- band assembly on the encoding GPU ------------------------------------------------------------
+__global__ void assemble_kernel(const uchar4* __restrict__ packed, int rows_per_rank, int w, int h, int nranks,
+                                int group, uchar4* __restrict__ frame) {
+    const size_t n = (size_t)w * h;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / w), x = (int)(i - (size_t)y * w);
+        const int g = y / group, rank = g % nranks, lg = g / nranks;
+        const int ly = lg * group + (y - g * group);
+        frame[(size_t)(h - 1 - y) * w + x] = packed[((size_t)rank * rows_per_rank + ly) * w + x];
+    }
+}
+
+// ---- probe kernels ---------------------------------------------------------------------------------
+__device__ __forceinline__ V3 ld3(const float* a, int i) { return mk(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+__device__ __forceinline__ void st3(float* a, int i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
+
+__global__ void k_acc(Consts C, int n, const float* q, const float* v, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st3(out, i, C.spin_a != 0.0f ? rrt::geodesic_acc<true>(C, ld3(q, i), ld3(v, i))
+                                            : rrt::geodesic_acc<false>(C, ld3(q, i), ld3(v, i)));
+}
+__global__ void k_rk4(Consts C, int n, float* p, float* v, const float* h) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 pp = ld3(p, i), vv = ld3(v, i);
+    float hi = h[i], r2 = rrt::dot3(pp, pp);
+    if (C.spin_a != 0.0f) rrt::rk4_step<true>(C, pp, vv, hi, hi * 0.5f, hi / 6.0f, r2, sqrtf(r2));
+    else rrt::rk4_step<false>(C, pp, vv, hi, hi * 0.5f, hi / 6.0f, r2, sqrtf(r2));
+    st3(p, i, pp);
+    st3(v, i, vv);
+}
+__global__ void k_euler(Consts C, int n, float* p, float* v, const float* h) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 pp = ld3(p, i), vv = ld3(v, i);
+    if (C.spin_a != 0.0f) rrt::euler_step<true>(C, pp, vv, h[i]);
+    else rrt::euler_step<false>(C, pp, vv, h[i]);
+    st3(p, i, pp);
+    st3(v, i, vv);
+}
+__global__ void k_redshift(Consts C, int n, const float* q, const float* v, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::redshift(C, ld3(q, i), ld3(v, i));
+}
+__global__ void k_hash31(int n, const float* p, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::hash31(ld3(p, i));
+}
+__global__ void k_noise3d(int n, const float* p, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::noise3d(ld3(p, i));
+}
+__global__ void k_fbm(int n, const float* p, int oct, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::fbm_rt(ld3(p, i), oct);
+}
+__global__ void k_disk_temp(Consts C, int n, const float* r, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::disk_temperature(C, r[i]);
+}
+__global__ void k_disk_density(Consts C, int n, const float* q, float time, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::disk_density(C, ld3(q, i), time);
+}
+__global__ void k_dust_density(Consts C, int n, const float* q, float time, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::dust_density(C, ld3(q, i), time);
+}
+__global__ void k_sky(cudaTextureObject_t sky, int n, const float* tx, const float* ty, float4* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex2D<float4>(sky, tx[i], ty[i]);
+}
+
+// FP32 roofline probe: 8 independent FFMA chains per thread, all operands in registers.
+__global__ void __launch_bounds__(256) k_fp32_peak(int iters, float seed, float* sink) {
+    float a0 = seed, a1 = seed + 1.f, a2 = seed + 2.f, a3 = seed + 3.f, a4 = seed + 4.f, a5 = seed + 5.f, a6 = seed + 6.f,
+          a7 = seed + 7.f;
+    const float m = 0.999f + seed * 1e-9f, c = 1e-3f + seed;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = __fmaf_rn(a0, m, c); a1 = __fmaf_rn(a1, m, c); a2 = __fmaf_rn(a2, m, c); a3 = __fmaf_rn(a3, m, c);
+            a4 = __fmaf_rn(a4, m, c); a5 = __fmaf_rn(a5, m, c); a6 = __fmaf_rn(a6, m, c); a7 = __fmaf_rn(a7, m, c);
+        }
+    }
+    float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123456.789f) sink[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace
+
+// =================================== host side: context + C ABI ===================================
+
+struct rrt_context {
+    int device = -1;
+    int sm_count = 0;
+    unsigned long long* d_counters = nullptr;
+    unsigned int* d_tickets = nullptr;
+    unsigned ticket_next = 0;
+    void* d_frame = nullptr;
+    size_t d_frame_bytes = 0;
+    std::string err;
+    std::mutex mu;
+};
+struct rrt_sky {
+    int device = -1;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+};
+
+namespace {
+constexpr unsigned kTicketRing = 1024;
+thread_local std::string g_create_err;
+
+int fail(rrt_context* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+    std::string m = what;
+    if (e != cudaSuccess) { m += ": "; m += cudaGetErrorString(e); }
+    if (ctx) ctx->err = m; else g_create_err = m;
+    return code;
+}
+#define RRT_CU(ctx, call)                                                    \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return fail(ctx, RRT_ERR_CUDA, #call, e__);  \
+    } while (0)
+
+// Derived constants in float, with the reference's own association (see rrt_device.cuh::Consts).
+Consts make_consts(const rrt_params& P) {
+    Consts C;
+    std::memset(&C, 0, sizeof(C));
+    C.horizon_r = P.event_horizon * 1.01f;
+    C.acc_rmin = P.event_horizon * 0.5f;
+    C.radial_k = -1.5f * P.event_horizon;
+    C.drag_k = (2.0f * P.spin_a) * P.event_horizon;
+    C.spin_a = P.spin_a;
+    C.event_horizon = P.event_horizon;
+    C.disk_zone_y = P.disk_h * 5.0f;
+    C.disk_zone_r = P.disk_out + 5.0f;
+    C.dust_zone_y = P.cloud_h * 1.5f;
+    C.dust_zone_r = P.cloud_out;
+    const float scale[4] = {1.0f, 0.1f, 0.3f, 0.5f};
+    for (int i = 0; i < 4; ++i) {
+        volatile float h = P.step_size;  // volatile: keep every intermediate in binary32
+        if (i) h = h * scale[i];
+        C.h[i] = h;
+        volatile float hh = h * 0.5f;
+        volatile float h6 = h / 6.0f;
+        C.hh[i] = hh;
+        C.h6[i] = h6;
+    }
+    C.isco = P.isco_radius;
+    C.disk_out = P.disk_out;
+    C.disk_h = P.disk_h;
+    volatile float tf = P.disk_out * 0.85f;
+    volatile float ts = P.disk_out - tf;
+    C.taper_from = tf;
+    C.taper_span = ts;
+    C.dust_e1 = P.disk_out * 0.8f;
+    C.dust_in_e1 = P.isco_radius + 5.0f;
+    C.cloud_hh = P.cloud_h * 0.5f;
+    C.disk_temp_ref = P.disk_temp_ref;
+    C.disk_luminosity = P.disk_luminosity;
+    C.disk_opacity = P.disk_opacity;
+    C.cloud_luminosity = P.cloud_luminosity;
+    C.cloud_opacity = P.cloud_opacity;
+    C.exposure = P.exposure;
+    C.max_steps = P.max_steps;
+    C.flags = P.flags;
+    return C;
+}
+
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// RAII device buffer for the probes
+struct DBuf {
+    void* p = nullptr;
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    ~DBuf() { if (p) cudaFree(p); }
+};
+
+template <typename K, typename... Args>
+int run_probe(rrt_context* ctx, int n, K kernel, Args... args) {
+    if (n > 0) kernel<<<(n + 127) / 128, 128>>>(args...);
+    RRT_CU(ctx, cudaGetLastError());
+    RRT_CU(ctx, cudaDeviceSynchronize());
+    return RRT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rrt_abi_version(void) { return RRT_ABI_VERSION; }
+
+const char* rrt_build_info(void) {
+    return "librrt_b200 abi=1 arch=sm_100a fmad=false prec-div=true prec-sqrt=true ftz=false (nvcc "
+#define RRT_STR2(x) #x
+#define RRT_STR(x) RRT_STR2(x)
+           RRT_STR(__CUDACC_VER_MAJOR__) "." RRT_STR(__CUDACC_VER_MINOR__) ")";
+}
+
+const char* rrt_last_error(const rrt_context* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int rrt_context_create(int device, rrt_context** out) {
+    if (!out) return fail(nullptr, RRT_ERR_BAD_ARG, "rrt_context_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, RRT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU fallback)", e);
+    if (device < 0 || device >= ndev) return fail(nullptr, RRT_ERR_BAD_ARG, "rrt_context_create: bad device ordinal");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, RRT_ERR_CUDA, "cudaGetDeviceProperties", e);
+    if (prop.major != 10) return fail(nullptr, RRT_ERR_NO_DEVICE, "device is not compute capability 10.x (library is built for sm_100a only)");
+    rrt_context* ctx = new (std::nothrow) rrt_context();
+    if (!ctx) return fail(nullptr, RRT_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    DevGuard g(device);
+    if ((e = cudaMalloc(&ctx->d_counters, sizeof(rrt_counters))) != cudaSuccess ||
+        (e = cudaMemset(ctx->d_counters, 0, sizeof(rrt_counters))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_tickets, kTicketRing * sizeof(unsigned))) != cudaSuccess ||
+        (e = cudaMemset(ctx->d_tickets, 0, kTicketRing * sizeof(unsigned))) != cudaSuccess) {
+        fail(nullptr, RRT_ERR_CUDA, "context allocation", e);
+        rrt_context_destroy(ctx);
+        return RRT_ERR_CUDA;
+    }
+    *out = ctx;
+    return RRT_OK;
+}
+
+void rrt_context_destroy(rrt_context* ctx) {
+    if (!ctx) return;
+    DevGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+    if (ctx->d_frame) cudaFree(ctx->d_frame);
+    delete ctx;
+}
+
+void rrt_default_params(rrt_params* o) {  // include/config.h
+    if (!o) return;
+    o->spin_a = 0.0f;
+    o->event_horizon = 2.0f;
+    o->isco_radius = 10.0f;
+    o->disk_out = 25.0f;
+    o->disk_h = 0.8f;
+    o->disk_luminosity = 6.0f;
+    o->disk_opacity = 0.4f;
+    o->exposure = 0.8f;
+    o->cloud_h = 0.5f;
+    o->cloud_out = 25.0f;
+    o->cloud_opacity = 0.3f;
+    o->cloud_luminosity = 0.4f;
+    o->step_size = 0.3f;
+    o->disk_temp_ref = 1.5e7f;
+    o->max_steps = 2000;
+    o->flags = RRT_FLAG_DISK | RRT_FLAG_DUST;
+}
+
+void rrt_default_effects(rrt_effects* o) {  // camera_settings.h:5-16
+    if (!o) return;
+    o->use_bloom = 1; o->bloom_threshold = 0.8f; o->bloom_intensity = 0.5f;
+    o->use_vignette = 1; o->vignette_intensity = 0.4f;
+    o->use_ca = 0; o->ca_amount = 0.005f;
+    o->use_lens = 1; o->distortion_amount = 0.15f;
+}
+
+int rrt_sky_create(rrt_context* ctx, const uint8_t* host_rgba, int w, int h, rrt_sky** out) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!host_rgba || !out || w <= 0 || h <= 0) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_sky_create: bad argument");
+    *out = nullptr;
+    DevGuard g(ctx->device);
+    rrt_sky* s = new (std::nothrow) rrt_sky();
+    if (!s) return fail(ctx, RRT_ERR_NOMEM, "out of host memory");
+    s->device = ctx->device;
+    // same recipe as the reference's loadSkybox (src/main.cpp:246-263)
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc(8, 8, 8, 8, cudaChannelFormatKindUnsigned);
+    cudaError_t e = cudaMallocArray(&s->arr, &desc, (size_t)w, (size_t)h);
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DToArray(s->arr, 0, 0, host_rgba, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cudaResourceDesc rd;
+        std::memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = s->arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = cudaAddressModeWrap;
+        td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        e = cudaCreateTextureObject(&s->tex, &rd, &td, nullptr);
+    }
+    if (e != cudaSuccess) {
+        fail(ctx, RRT_ERR_CUDA, "rrt_sky_create", e);
+        rrt_sky_destroy(s);
+        return RRT_ERR_CUDA;
+    }
+    *out = s;
+    return RRT_OK;
+}
+
+uint64_t rrt_sky_texture(const rrt_sky* sky) { return sky ? (uint64_t)sky->tex : 0; }
+
+void rrt_sky_destroy(rrt_sky* s) {
+    if (!s) return;
+    DevGuard g(s->device);
+    if (s->tex) cudaDestroyTextureObject(s->tex);
+    if (s->arr) cudaFreeArray(s->arr);
+    delete s;
+}
+
+int rrt_band_rows(const rrt_band* band, int h) {
+    if (h <= 0) return 0;
+    if (!band) return h;
+    if (band->nranks <= 0 || band->group <= 0 || band->rank < 0 || band->rank >= band->nranks) return RRT_ERR_BAD_ARG;
+    const int ngroups = (h + band->group - 1) / band->group;
+    int rows = 0;
+    for (int g = band->rank; g < ngroups; g += band->nranks) {
+        int y0 = g * band->group, y1 = y0 + band->group;
+        if (y1 > h) y1 = h;
+        rows += y1 - y0;
+    }
+    return rows;
+}
+
+int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx, uint64_t sky_texture,
+               float time, int w, int h, const rrt_band* band, void* d_out, int out_layout, const rrt_planes* planes,
+               void* stream) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!prm || !cam || !fx || w <= 0 || h <= 0 || sky_texture == 0 || prm->max_steps < 0 ||
+        (out_layout != RRT_OUT_FRAME && out_layout != RRT_OUT_PACKED) || (!d_out && !planes))
+        return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render: bad argument");
+    rrt_band b = {0, 1, 1};
+    if (band) b = *band;
+    const int local_rows = rrt_band_rows(&b, h);
+    if (local_rows < 0) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render: bad band");
+    if (local_rows == 0) return RRT_OK;
+
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    FrameArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.C = make_consts(*prm);
+    A.cam = *cam;
+    A.fx = *fx;
+    A.time = time;
+    A.w = w;
+    A.h = h;
+    A.band_rank = b.rank;
+    A.band_nranks = b.nranks;
+    A.band_group = b.group;
+    A.local_rows = local_rows;
+    A.out_layout = out_layout;
+    A.out = (uchar4*)d_out;
+    if (planes) A.planes = *planes;
+    A.sky = (cudaTextureObject_t)sky_texture;
+    A.counters = ctx->d_counters;
+    A.ticket = ctx->d_tickets + (ctx->ticket_next++ % kTicketRing);
+    RRT_CU(ctx, cudaMemsetAsync(A.ticket, 0, sizeof(unsigned), st));
+
+    const bool spin = prm->spin_a != 0.0f;
+    const bool media = (prm->flags & (RRT_FLAG_DISK | RRT_FLAG_DUST)) != 0;
+    void (*kern)(const FrameArgs) = spin ? (media ? render_kernel<true, true> : render_kernel<true, false>)
+                                         : (media ? render_kernel<false, true> : render_kernel<false, false>);
+    int per_sm = 0;
+    RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long ntiles = (long long)((w + kTileW - 1) / kTileW) * ((local_rows + kTileH - 1) / kTileH);
+    long long grid = (long long)ctx->sm_count * per_sm;
+    const long long need = (ntiles + (kBlock / 32) - 1) / (kBlock / 32);
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, kBlock, 0, st>>>(A);
+    RRT_CU(ctx, cudaGetLastError());
+    return RRT_OK;
+}
+
+int rrt_render_host(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
+                    uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!host_rgba || w <= 0 || h <= 0) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render_host: bad argument");
+    const size_t bytes = (size_t)w * h * 4;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        DevGuard g(ctx->device);
+        if (ctx->d_frame_bytes < bytes) {
+            if (ctx->d_frame) cudaFree(ctx->d_frame);
+            ctx->d_frame = nullptr;
+            ctx->d_frame_bytes = 0;
+            RRT_CU(ctx, cudaMalloc(&ctx->d_frame, bytes));
+            ctx->d_frame_bytes = bytes;
+        }
+    }
+    int rc = rrt_render(ctx, prm, cam, fx, sky_texture, time, w, h, nullptr, ctx->d_frame, RRT_OUT_FRAME, nullptr, nullptr);
+    if (rc != RRT_OK) return rc;
+    DevGuard g(ctx->device);
+    RRT_CU(ctx, cudaMemcpy(host_rgba, ctx->d_frame, bytes, cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+int rrt_assemble_bands(rrt_context* ctx, const void* d_packed, int rows_per_rank, int w, int h, int nranks, int group,
+                       void* d_frame, void* stream) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!d_packed || !d_frame || w <= 0 || h <= 0 || nranks <= 0 || group <= 0 || rows_per_rank <= 0)
+        return fail(ctx, RRT_ERR_BAD_ARG, "rrt_assemble_bands: bad argument");
+    DevGuard g(ctx->device);
+    assemble_kernel<<<ctx->sm_count * 8, 256, 0, (cudaStream_t)stream>>>((const uchar4*)d_packed, rows_per_rank, w, h,
+                                                                         nranks, group, (uchar4*)d_frame);
+    RRT_CU(ctx, cudaGetLastError());
+    return RRT_OK;
+}
+
+int rrt_read_counters(rrt_context* ctx, rrt_counters* out, int reset) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!out) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_read_counters: out is NULL");
+    DevGuard g(ctx->device);
+    RRT_CU(ctx, cudaDeviceSynchronize());
+    RRT_CU(ctx, cudaMemcpy(out, ctx->d_counters, sizeof(rrt_counters), cudaMemcpyDeviceToHost));
+    if (reset) RRT_CU(ctx, cudaMemset(ctx->d_counters, 0, sizeof(rrt_counters)));
+    return RRT_OK;
+}
+
+// ---- probes -----------------------------------------------------------------------------------------
+#define PROBE_PROLOGUE(cond)                                                  \
+    if (!ctx) return RRT_ERR_BAD_ARG;                                         \
+    if (!(cond) || n < 0) return fail(ctx, RRT_ERR_BAD_ARG, "probe: bad argument"); \
+    DevGuard g__(ctx->device);
+
+int rrt_geodesic_acc_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, const float* v, float* out) {
+    PROBE_PROLOGUE(prm && q && v && out)
+    DBuf dq, dv, dout;
+    const size_t b = (size_t)n * 3 * sizeof(float);
+    RRT_CU(ctx, dq.alloc(b)); RRT_CU(ctx, dv.alloc(b)); RRT_CU(ctx, dout.alloc(b));
+    RRT_CU(ctx, cudaMemcpy(dq.p, q, b, cudaMemcpyHostToDevice));
+    RRT_CU(ctx, cudaMemcpy(dv.p, v, b, cudaMemcpyHostToDevice));
+    int rc = run_probe(ctx, n, k_acc, make_consts(*prm), n, (const float*)dq.p, (const float*)dv.p, (float*)dout.p);
+    if (rc) return rc;
+    RRT_CU(ctx, cudaMemcpy(out, dout.p, b, cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+static int step_batch(rrt_context* ctx, const rrt_params* prm, int n, float* p, float* v, const float* h, bool rk4) {
+    PROBE_PROLOGUE(prm && p && v && h)
+    DBuf dp, dv, dh;
+    const size_t b = (size_t)n * 3 * sizeof(float);
+    RRT_CU(ctx, dp.alloc(b)); RRT_CU(ctx, dv.alloc(b)); RRT_CU(ctx, dh.alloc((size_t)n * sizeof(float)));
+    RRT_CU(ctx, cudaMemcpy(dp.p, p, b, cudaMemcpyHostToDevice));
+    RRT_CU(ctx, cudaMemcpy(dv.p, v, b, cudaMemcpyHostToDevice));
+    RRT_CU(ctx, cudaMemcpy(dh.p, h, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = run_probe(ctx, n, rk4 ? k_rk4 : k_euler, make_consts(*prm), n, (float*)dp.p, (float*)dv.p, (const float*)dh.p);
+    if (rc) return rc;
+    RRT_CU(ctx, cudaMemcpy(p, dp.p, b, cudaMemcpyDeviceToHost));
+    RRT_CU(ctx, cudaMemcpy(v, dv.p, b, cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+int rrt_rk4_step_batch(rrt_context* ctx, const rrt_params* prm, int n, float* p, float* v, const float* h) {
+    return step_batch(ctx, prm, n, p, v, h, true);
+}
+int rrt_euler_step_batch(rrt_context* ctx, const rrt_params* prm, int n, float* p, float* v, const float* h) {
+    return step_batch(ctx, prm, n, p, v, h, false);
+}
+
+int rrt_redshift_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, const float* v, float* out) {
+    PROBE_PROLOGUE(prm && q && v && out)
+    DBuf dq, dv, dout;
+    const size_t b = (size_t)n * 3 * sizeof(float);
+    RRT_CU(ctx, dq.alloc(b)); RRT_CU(ctx, dv.alloc(b)); RRT_CU(ctx, dout.alloc((size_t)n * sizeof(float)));
+    RRT_CU(ctx, cudaMemcpy(dq.p, q, b, cudaMemcpyHostToDevice));
+    RRT_CU(ctx, cudaMemcpy(dv.p, v, b, cudaMemcpyHostToDevice));
+    int rc = run_probe(ctx, n, k_redshift, make_consts(*prm), n, (const float*)dq.p, (const float*)dv.p, (float*)dout.p);
+    if (rc) return rc;
+    RRT_CU(ctx, cudaMemcpy(out, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+}  // extern "C"
+// scalar-of-float3 probes share one shape: p[3n] -> out[n]
+template <typename Launch>
+static int p3_to_scalar(rrt_context* ctx, int n, const float* p, float* out, Launch launch) {
+    PROBE_PROLOGUE(p && out)
+    DBuf dp, dout;
+    RRT_CU(ctx, dp.alloc((size_t)n * 3 * sizeof(float))); RRT_CU(ctx, dout.alloc((size_t)n * sizeof(float)));
+    RRT_CU(ctx, cudaMemcpy(dp.p, p, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = launch((const float*)dp.p, (float*)dout.p);
+    if (rc) return rc;
+    RRT_CU(ctx, cudaMemcpy(out, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+extern "C" {
+int rrt_hash31_batch(rrt_context* ctx, int n, const float* p, float* out) {
+    return p3_to_scalar(ctx, n, p, out, [&](const float* dp, float* dout) { return run_probe(ctx, n, k_hash31, n, dp, dout); });
+}
+int rrt_noise3d_batch(rrt_context* ctx, int n, const float* p, float* out) {
+    return p3_to_scalar(ctx, n, p, out, [&](const float* dp, float* dout) { return run_probe(ctx, n, k_noise3d, n, dp, dout); });
+}
+int rrt_fbm_batch(rrt_context* ctx, int n, const float* p, int octaves, float* out) {
+    if (octaves < 0 || octaves > 16) return ctx ? fail(ctx, RRT_ERR_BAD_ARG, "rrt_fbm_batch: octaves out of range") : RRT_ERR_BAD_ARG;
+    return p3_to_scalar(ctx, n, p, out, [&](const float* dp, float* dout) { return run_probe(ctx, n, k_fbm, n, dp, octaves, dout); });
+}
+int rrt_disk_density_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, float time, float* out) {
+    if (!prm) return ctx ? fail(ctx, RRT_ERR_BAD_ARG, "probe: bad argument") : RRT_ERR_BAD_ARG;
+    Consts C = make_consts(*prm);
+    return p3_to_scalar(ctx, n, q, out, [&](const float* dp, float* dout) { return run_probe(ctx, n, k_disk_density, C, n, dp, time, dout); });
+}
+int rrt_dust_density_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* q, float time, float* out) {
+    if (!prm) return ctx ? fail(ctx, RRT_ERR_BAD_ARG, "probe: bad argument") : RRT_ERR_BAD_ARG;
+    Consts C = make_consts(*prm);
+    return p3_to_scalar(ctx, n, q, out, [&](const float* dp, float* dout) { return run_probe(ctx, n, k_dust_density, C, n, dp, time, dout); });
+}
+int rrt_disk_temperature_batch(rrt_context* ctx, const rrt_params* prm, int n, const float* r, float* out) {
+    PROBE_PROLOGUE(prm && r && out)
+    DBuf dr, dout;
+    RRT_CU(ctx, dr.alloc((size_t)n * sizeof(float))); RRT_CU(ctx, dout.alloc((size_t)n * sizeof(float)));
+    RRT_CU(ctx, cudaMemcpy(dr.p, r, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = run_probe(ctx, n, k_disk_temp, make_consts(*prm), n, (const float*)dr.p, (float*)dout.p);
+    if (rc) return rc;
+    RRT_CU(ctx, cudaMemcpy(out, dout.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+int rrt_sky_sample_batch(rrt_context* ctx, uint64_t sky_texture, int n, const float* tx, const float* ty, float* out4) {
+    PROBE_PROLOGUE(sky_texture && tx && ty && out4)
+    DBuf dx, dy, dout;
+    RRT_CU(ctx, dx.alloc((size_t)n * sizeof(float))); RRT_CU(ctx, dy.alloc((size_t)n * sizeof(float)));
+    RRT_CU(ctx, dout.alloc((size_t)n * 4 * sizeof(float)));
+    RRT_CU(ctx, cudaMemcpy(dx.p, tx, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    RRT_CU(ctx, cudaMemcpy(dy.p, ty, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = run_probe(ctx, n, k_sky, (cudaTextureObject_t)sky_texture, n, (const float*)dx.p, (const float*)dy.p, (float4*)dout.p);
+    if (rc) return rc;
+    RRT_CU(ctx, cudaMemcpy(out4, dout.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+int rrt_fp32_peak_probe(rrt_context* ctx, int iters, double* tflops, double* ms_out) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (iters <= 0 || !tflops) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_fp32_peak_probe: bad argument");
+    DevGuard g(ctx->device);
+    DBuf sink;
+    RRT_CU(ctx, sink.alloc(sizeof(float)));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    RRT_CU(ctx, cudaEventCreate(&e0));
+    RRT_CU(ctx, cudaEventCreate(&e1));
+    k_fp32_peak<<<blocks, threads>>>(iters / 8 + 1, 1.0f, (float*)sink.p);  // warm-up
+    double best = 1e30;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        k_fp32_peak<<<blocks, threads>>>(iters, 1.0f, (float*)sink.p);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(ctx, RRT_ERR_CUDA, "fp32 probe", e); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flop = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 2.0;
+    *tflops = flop / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return RRT_OK;
+}
+
+}  // extern "C"
