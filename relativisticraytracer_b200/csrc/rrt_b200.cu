@@ -56,6 +56,17 @@ struct RayResult {
     bool captured, touched, exhausted;
 };
 
+// General-domain RK4 step (guarded div/sqrt, r < acc_rmin select): the rarely taken fallback of the loop.
+struct PV {
+    V3 p, v;
+};
+template <bool SPIN>
+__device__ __noinline__ PV rk4_step_general(const Consts& C, V3 p, V3 v, float h, float hh, float h6) {
+    const float r2 = rrt::dot3(p, p);
+    rrt::rk4_step<SPIN>(C, p, v, h, hh, h6, r2, sqrtf(r2));
+    return PV{p, v};
+}
+
 // One ray: reference raymarch_kernel lines 20-150.
 template <bool SPIN, bool MEDIA>
 __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayResult& R) {
@@ -83,18 +94,34 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
     unsigned n_disk = 0, n_dust = 0, n_dense = 0;
     const int max_steps = C.max_steps;
     const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
+    // Domain of the branch-free div/sqrt (rrt_device.cuh): a ray that starts absurdly far out takes the
+    // general path for its whole life.  Uniform per launch in practice (depends on the camera only).
+    const bool fast_ok = rrt::dot3(p, p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
+    const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
 #pragma unroll 1
     for (; it < max_steps; ++it) {                                                        // :41
         const float r2 = rrt::dot3(p, p);
-        const float r = sqrtf(r2);                                                        // :44
+        const float r = rrt::sqrt_rn_fast(r2);                                            // :44
         if (r < C.horizon_r) { captured = true; T = 0.0f; break; }                        // :47-51
-        const bool near_bh = r < 18.0f;                                                   // :56
-        const bool disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;           // :57
-        const bool dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;           // :58
-        const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));               // :60-62
-        const float h = C.h[zi];
+        bool disk_zone = false, dust_zone = false;
+        float h = C.h[0], h6 = C.h6[0];
+        if (r < zone_rmax) {  // 3/4 of all steps are outside every zone: one compare for them
+            const bool near_bh = r < 18.0f;                                               // :56
+            disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;                  // :57
+            dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;                  // :58
+            const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));           // :60-62
+            h = C.h[zi];
+            h6 = C.h6[zi];
+        }
+        const float hh = h * 0.5f;  // exact
         const V3 q = p;  // pre-step position: media and the escape test use it (:68-69, :120)
-        rrt::rk4_step<SPIN>(C, p, v, h, C.hh[zi], C.h6[zi], r2, r);                       // :64
+        const V3 v_in = v;
+        const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);           // :64
+        if (!fast_ok || rmin < C.acc_rmin) {
+            // outside the branch-free domain, or geodesics.h:33 can fire: redo this step with the general code
+            const PV s = rk4_step_general<SPIN>(C, q, v_in, h, hh, h6);
+            p = s.p; v = s.v;
+        }
         if (MEDIA && (disk_zone || dust_zone)) {                                          // :67
             float dd = 0.0f, dc = 0.0f;
             if (disk_zone && want_disk) { dd = rrt::disk_density(C, q, A.time); ++n_disk; }
@@ -317,6 +344,32 @@ __global__ void k_dust_density(Consts C, int n, const float* q, float time, floa
 __global__ void k_sky(cudaTextureObject_t sky, int n, const float* tx, const float* ty, float4* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = tex2D<float4>(sky, tx[i], ty[i]);
+}
+
+// div_rn_fast / sqrt_rn_fast vs the IEEE intrinsics on random operands of the render loop's domain.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float make_float(unsigned mant_bits, int exp2, bool neg) {
+    return __uint_as_float((neg ? 0x80000000u : 0u) | ((unsigned)(exp2 + 127) << 23) | (mant_bits & 0x7fffffu));
+}
+__global__ void k_exact_math(unsigned long long seed, unsigned long long n, unsigned long long* bad) {
+    unsigned long long bad_div = 0, bad_sqrt = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long a = mix64(seed + 2 * i), b = mix64(seed + 2 * i + 1);
+        // numerator: 0 (1/64 of draws) or +-2^[-60,40]; denominator: +-2^[-20,62]; sqrt argument: 2^[-40,80]
+        float x = make_float((unsigned)a, (int)((a >> 23) % 101) - 60, (a >> 40) & 1);
+        if (((a >> 41) & 63) == 0) x = 0.0f;
+        const float y = make_float((unsigned)b, (int)((b >> 23) % 83) - 20, (b >> 40) & 1);
+        const float s = make_float((unsigned)(a >> 8), (int)((b >> 41) % 121) - 40, false);
+        if (!(rrt::div_rn_fast(x, y) == __fdiv_rn(x, y))) ++bad_div;
+        if (!(rrt::sqrt_rn_fast(s) == __fsqrt_rn(s))) ++bad_sqrt;
+    }
+    if (bad_div) atomicAdd(bad + 0, bad_div);
+    if (bad_sqrt) atomicAdd(bad + 1, bad_sqrt);
 }
 
 // FP32 roofline probe: 8 independent FFMA chains per thread, all operands in registers.
@@ -783,6 +836,23 @@ int rrt_sky_sample_batch(rrt_context* ctx, uint64_t sky_texture, int n, const fl
     int rc = run_probe(ctx, n, k_sky, (cudaTextureObject_t)sky_texture, n, (const float*)dx.p, (const float*)dy.p, (float4*)dout.p);
     if (rc) return rc;
     RRT_CU(ctx, cudaMemcpy(out4, dout.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+int rrt_exact_math_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_t* div_mismatches, uint64_t* sqrt_mismatches) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!div_mismatches || !sqrt_mismatches) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_exact_math_selftest: bad argument");
+    DevGuard g(ctx->device);
+    DBuf bad;
+    RRT_CU(ctx, bad.alloc(2 * sizeof(unsigned long long)));
+    RRT_CU(ctx, cudaMemset(bad.p, 0, 2 * sizeof(unsigned long long)));
+    k_exact_math<<<ctx->sm_count * 16, 256>>>((unsigned long long)seed, (unsigned long long)n, (unsigned long long*)bad.p);
+    RRT_CU(ctx, cudaGetLastError());
+    RRT_CU(ctx, cudaDeviceSynchronize());
+    unsigned long long h[2] = {0, 0};
+    RRT_CU(ctx, cudaMemcpy(h, bad.p, sizeof(h), cudaMemcpyDeviceToHost));
+    *div_mismatches = h[0];
+    *sqrt_mismatches = h[1];
     return RRT_OK;
 }
 

@@ -186,6 +186,12 @@ class Renderer:
         self._check(self._lib.rrt_fp32_peak_probe(self._ctx, int(iters), C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
+    def exact_math_selftest(self, seed: int = 1, n: int = 1 << 30):
+        """(div mismatches, sqrt mismatches) of the loop's branch-free div/sqrt vs the IEEE intrinsics."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.rrt_exact_math_selftest(self._ctx, C.c_uint64(seed), C.c_uint64(n), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     # ---- function-level probes (host numpy in / out) --------------------------------------------------
     @staticmethod
     def _f32(a):
