@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--flags", type=int, default=3, help="experiment only: media flags (3 = disk+dust = the headline workload)")
+    ap.add_argument("--camera", default="C0", help="experiment only: C0 (headline) .. C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     return ap.parse_args()
@@ -177,8 +179,10 @@ def main():
 
     r = rrt.Renderer(dev)
     sky = r.create_sky(rrt.procedural_sky(4096, 2048))
-    prm = rrt.default_params(spin_a=SPIN)
-    cam = rrt.camera_state_from(CAM_POS, CAM_YAW, CAM_PITCH)
+    prm = rrt.default_params(spin_a=SPIN, flags=args.flags)
+    cams = {"C0": (CAM_POS, CAM_YAW, CAM_PITCH), "C1": ((15.0, 3.0, -30.0), -26.6, -5.1),
+            "C2": ((35.0, 0.8, 10.0), -106.0, -1.2), "C3": ((4.2, 0.6, 4.2), -90.0, -5.7)}
+    cam = rrt.camera_state_from(*cams[args.camera])
     fx = rrt.default_effects()
     band = rrt.Band(rank, world, BAND_GROUP)
     rows_mine = r.band_rows(band, h)
@@ -298,7 +302,7 @@ def main():
         "metric": "geodesic_rk4_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if (w, h) == (W4K, H4K) else f"{w}x{h} variant of: {WORKLOAD}",
+        "config": {"workload": WORKLOAD if (w, h, args.flags, args.camera) == (W4K, H4K, 3, "C0") else f"EXPERIMENT {w}x{h} flags={args.flags} camera={args.camera} variant of: {WORKLOAD}",
                    "width": w, "height": h, "spin_a": SPIN, "media": "disk+dust", "camera": "C0", "band_group_rows": BAND_GROUP,
                    "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) between timed steps",
                    "rk4_steps_per_frame": rk4_per_frame, "disk_evals_per_frame": disk_evals, "dust_evals_per_frame": dust_evals},

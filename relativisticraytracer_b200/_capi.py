@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "librrt_b200.so")
+LIB_PATH = os.environ.get("RRT_B200_LIB") or os.path.join(PKG_DIR, "librrt_b200.so")   # env: A/B builds only
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM = 0, -1, -2, -3, -4
 FLAG_DISK, FLAG_DUST = 1, 2

@@ -46,6 +46,9 @@ struct FrameArgs {
 
 constexpr int kTileW = 8, kTileH = 4;  // one warp = 8x4 pixels
 constexpr int kBlock = 128;
+#ifndef RRT_MIN_BLOCKS
+#define RRT_MIN_BLOCKS 1
+#endif
 
 struct RayResult {
     float hdr[3], T, I[3];
@@ -65,6 +68,47 @@ __device__ __noinline__ PV rk4_step_general(const Consts& C, V3 p, V3 v, float h
     const float r2 = rrt::dot3(p, p);
     rrt::rk4_step<SPIN>(C, p, v, h, hh, h6, r2, sqrtf(r2));
     return PV{p, v};
+}
+
+// One in-zone sample of the participating media: densities at the PRE-step position, redshift with the
+// POST-step velocity, emission colour and the step transmittance (reference raymarcher.cu:67-108).  Kept
+// out of line so the vacuum step loop stays a few KB of straight-line FMA code in the instruction cache.
+struct MediaOut {
+    float er, eg, eb, s;
+    int dense;
+};
+__device__ __noinline__ MediaOut media_sample(const Consts& C, V3 q, V3 v, float r, float h, float time, unsigned zones) {
+    MediaOut o = {0.f, 0.f, 0.f, 1.0f, 0};
+    const float dd = (zones & 1u) ? rrt::disk_density(C, q, time) : 0.0f;                 // :68
+    const float dc = (zones & 2u) ? rrt::dust_density(C, q, time) : 0.0f;                 // :69
+    if (dd > 0.001f || dc > 0.001f) {                                                     // :71
+        o.dense = 1;
+        float er = 0.f, eg = 0.f, eb = 0.f, kappa = 0.f;
+        const float g = rrt::redshift(C, q, v);  // same arguments in both branches (:77, :92)
+        if (dd > 0.001f) {                                                                // :76-88
+            float Tk = rrt::disk_temperature(C, r);
+            float tn = rrt::t_powf(Tk / C.disk_temp_ref, 0.5f);
+            float bol = rrt::t_powf(g, 4.0f) * tn * dd * C.disk_luminosity;
+            float ct = g * rrt::t_powf(Tk / C.disk_temp_ref, 0.4f) * 2.5f;
+            er += 1.0f * bol;
+            eg += fminf(0.25f, 0.12f * ct) * bol;
+            eb += fmaxf(0.0f, 0.01f * (ct - 2.0f)) * bol;
+            kappa += dd * C.disk_opacity;
+        }
+        if (dc > 0.001f) {                                                                // :91-105
+            float light = 0.5f + 3.0f * rrt::t_powf(C.isco / fmaxf(r, C.isco), 1.2f);
+            float J = dc * C.cloud_luminosity * light;
+            float sh = rrt::sstep(0.7f, 1.3f, g);
+            er += 0.60f * J * rrt::mixf(1.2f, 0.8f, sh);
+            eg += 0.65f * J * rrt::mixf(0.8f, 1.1f, sh);
+            eb += 0.80f * J * rrt::mixf(0.6f, 1.4f, sh);
+            kappa += dc * C.cloud_opacity;
+        }
+        const float tau = kappa * h;                                                      // :107
+        o.s = rrt::t_expf(-tau);
+        o.er = er; o.eg = eg; o.eb = eb;
+    }
+    return o;
 }
 
 // One ray: reference raymarch_kernel lines 20-150.
@@ -123,38 +167,18 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             p = s.p; v = s.v;
         }
         if (MEDIA && (disk_zone || dust_zone)) {                                          // :67
-            float dd = 0.0f, dc = 0.0f;
-            if (disk_zone && want_disk) { dd = rrt::disk_density(C, q, A.time); ++n_disk; }
-            if (dust_zone && want_dust) { dc = rrt::dust_density(C, q, A.time); ++n_dust; }
-            if (dd > 0.001f || dc > 0.001f) {                                             // :71
-                touched = true;
-                ++n_dense;
-                float er = 0.f, eg = 0.f, eb = 0.f, kappa = 0.f;
-                const float g = rrt::redshift(C, q, v);  // same arguments in both branches (:77, :92)
-                if (dd > 0.001f) {                                                        // :76-88
-                    float Tk = rrt::disk_temperature(C, r);
-                    float tn = powf(Tk / C.disk_temp_ref, 0.5f);
-                    float bol = powf(g, 4.0f) * tn * dd * C.disk_luminosity;
-                    float ct = g * powf(Tk / C.disk_temp_ref, 0.4f) * 2.5f;
-                    er += 1.0f * bol;
-                    eg += fminf(0.25f, 0.12f * ct) * bol;
-                    eb += fmaxf(0.0f, 0.01f * (ct - 2.0f)) * bol;
-                    kappa += dd * C.disk_opacity;
+            const unsigned zones = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);
+            n_disk += zones & 1u;
+            n_dust += zones >> 1;
+            if (zones) {
+                const MediaOut m = media_sample(C, q, v, r, h, A.time, zones);
+                if (m.dense) {                                                            // :71
+                    touched = true;
+                    ++n_dense;
+                    const float wgt = (1.0f - m.s) * T;                                   // :109
+                    Ir += m.er * wgt; Ig += m.eg * wgt; Ib += m.eb * wgt;                 // :111-113
+                    T *= m.s;                                                             // :115
                 }
-                if (dc > 0.001f) {                                                        // :91-105
-                    float light = 0.5f + 3.0f * powf(C.isco / fmaxf(r, C.isco), 1.2f);
-                    float J = dc * C.cloud_luminosity * light;
-                    float sh = rrt::sstep(0.7f, 1.3f, g);
-                    er += 0.60f * J * rrt::mixf(1.2f, 0.8f, sh);
-                    eg += 0.65f * J * rrt::mixf(0.8f, 1.1f, sh);
-                    eb += 0.80f * J * rrt::mixf(0.6f, 1.4f, sh);
-                    kappa += dc * C.cloud_opacity;
-                }
-                float tau = kappa * h;                                                    // :107
-                float s = expf(-tau);
-                float wgt = (1.0f - s) * T;
-                Ir += er * wgt; Ig += eg * wgt; Ib += eb * wgt;                           // :111-113
-                T *= s;                                                                   // :115
             }
         }
         if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { escaped = true; ++it; break; }       // :120 (this step counted)
@@ -171,7 +195,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 }
 
 template <bool SPIN, bool MEDIA>
-__global__ void __launch_bounds__(kBlock) render_kernel(const __grid_constant__ FrameArgs A) {
+__global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ FrameArgs A) {
     const int lane = threadIdx.x & 31;
     const int ntx = (A.w + kTileW - 1) / kTileW;
     const int nty = (A.local_rows + kTileH - 1) / kTileH;
