@@ -184,32 +184,20 @@ def main():
             "C2": ((35.0, 0.8, 10.0), -106.0, -1.2), "C3": ((4.2, 0.6, 4.2), -90.0, -5.7)}
     cam = rrt.camera_state_from(*cams[args.camera])
     fx = rrt.default_effects()
-    band = rrt.Band(rank, world, BAND_GROUP)
-    rows_mine = r.band_rows(band, h)
-    rows_max = max(r.band_rows(rrt.Band(i, world, BAND_GROUP), h) for i in range(world))
-    packed = torch.zeros((rows_max, w, 4), dtype=torch.uint8, device="cuda")
-    gathered = torch.zeros((world, rows_max, w, 4), dtype=torch.uint8, device="cuda") if (world > 1 and rank == 0) else None
-    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    from relativisticraytracer_b200.parallel import BandedFrame
+    bf = BandedFrame(r, w, h, BAND_GROUP)
     host_frame = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     stream = torch.cuda.current_stream()
 
-    def one_frame(to_host: bool):
-        """the hot path for one step; returns number of OUR kernels launched"""
-        if world == 1:
-            if to_host:
-                r.render_host(prm, cam, fx, sky, TIME, w, h, host_frame)        # C-ABI call, host destination
-            else:
-                r.render(prm, cam, fx, sky, TIME, w, h, out=frame, layout=rrt.OUT_FRAME)
+    def one_frame(to_host: bool) -> int:
+        """the hot path for one step; returns the number of OUR kernels launched"""
+        if world == 1 and to_host:
+            r.render_host(prm, cam, fx, sky, TIME, w, h, host_frame)   # the C-ABI call with a HOST destination
             return 1
-        r.render(prm, cam, fx, sky, TIME, w, h, band=band, out=packed, layout=rrt.OUT_PACKED)
-        dist.gather(packed, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
-        n = 1
-        if rank == 0:
-            r.assemble_bands(gathered, rows_max, w, h, world, BAND_GROUP, frame=frame)
-            n += 1
-            if to_host:
-                host_frame.copy_(frame, non_blocking=True)
+        n = bf.render(prm, cam, fx, sky, TIME)                         # trace [+ NCCL gather + assemble on rank 0]
+        if to_host and rank == 0:
+            host_frame.copy_(bf.frame, non_blocking=True)
         return n
 
     def barrier():
@@ -218,7 +206,8 @@ def main():
         torch.cuda.synchronize()
 
     def timed(n_steps: int, to_host: bool):
-        """sum of per-step device times (CUDA events on the launching stream), L2 flushed between steps"""
+        """K steps, each bracketed by barrier + synchronize; device time from CUDA events on the launching
+        stream (host clock for the synchronous host-destination call); L2 flushed between steps."""
         total_ms, kernel_ms, launches = 0.0, 0.0, 0
         for _ in range(n_steps):
             flush.fill_(1)
@@ -227,25 +216,26 @@ def main():
             t0 = time.perf_counter()
             e0.record(stream)
             if world == 1 and to_host:
-                launches += one_frame(True)      # synchronous inside (D2H), host clock is the honest one
+                launches += one_frame(True)
                 torch.cuda.synchronize()
                 total_ms += (time.perf_counter() - t0) * 1e3
                 continue
             if world == 1:
-                launches += one_frame(False)
+                launches += one_frame(to_host)
                 e1.record(stream)
-                e2.record(stream)
             else:
-                r.render(prm, cam, fx, sky, TIME, w, h, band=band, out=packed, layout=rrt.OUT_PACKED)
+                r.render(prm, cam, fx, sky, TIME, w, h, band=bf.band, out=bf.packed, layout=rrt.OUT_PACKED)
                 e1.record(stream)
-                dist.gather(packed, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
                 launches += 1
                 if rank == 0:
-                    r.assemble_bands(gathered, rows_max, w, h, world, BAND_GROUP, frame=frame)
+                    dist.gather(bf.packed, list(bf.gathered.unbind(0)), dst=0)
+                    r.assemble_bands(bf.gathered, bf.rows_max, w, h, world, BAND_GROUP, frame=bf.frame)
                     launches += 1
                     if to_host:
-                        host_frame.copy_(frame, non_blocking=True)
-                e2.record(stream)
+                        host_frame.copy_(bf.frame, non_blocking=True)
+                else:
+                    dist.gather(bf.packed, None, dst=0)
+            e2.record(stream)
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e2)
             kernel_ms += e0.elapsed_time(e1)

@@ -194,7 +194,7 @@ float rrt_path_clock(int frame, float fps);
 int rrt_fp32_peak_probe(rrt_context* ctx, int iters, double* tflops, double* ms);
 
 /* Self-test of the branch-free correctly-rounded division / square root the render loop uses
- * (csrc/rrt_device.cuh: div_rn_fast, sqrt_rn_fast) against the IEEE intrinsics __fdiv_rn / __fsqrt_rn, on
+ * (include/rrt_device.cuh: div_rn_fast, sqrt_rn_fast) against the IEEE intrinsics __fdiv_rn / __fsqrt_rn, on
  * `n` pseudo-random operand pairs drawn on the device from the loop's operand domain.  Outputs the number
  * of results that differ in value (expected: 0 and 0). */
 int rrt_exact_math_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_t* div_mismatches,

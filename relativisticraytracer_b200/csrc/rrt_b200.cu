@@ -21,7 +21,7 @@
 #include <string>
 
 #include "../../include/rrt.h"
-#include "rrt_device.cuh"
+#include "../../include/rrt_device.cuh"
 
 using rrt::Consts;
 using rrt::V3;
@@ -208,7 +208,13 @@ __global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel(const __
         if (lane == 0) tile = atomicAdd(A.ticket, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
-        const int tx = (int)(tile % (unsigned)ntx), ty = (int)(tile / (unsigned)ntx);
+        // Tile rows are handed out from the image centre outwards: the rows that cross the hole and the
+        // disk are the expensive ones, so they start first and the cheap sky rows fill the tail of the launch.
+        const int tx = (int)(tile % (unsigned)ntx), k = (int)(tile / (unsigned)ntx);
+        const int c = nty >> 1, m = min(c, nty - 1 - c);
+        int ty;
+        if (k <= 2 * m) ty = (k & 1) ? c + ((k + 1) >> 1) : c - (k >> 1);
+        else ty = (c > nty - 1 - c) ? (c - m - 1) - (k - (2 * m + 1)) : (c + m + 1) + (k - (2 * m + 1));
         const int x = tx * kTileW + (lane & (kTileW - 1));
         const int ly = ty * kTileH + (lane >> 3);
         if (x >= A.w || ly >= A.local_rows) continue;
@@ -450,7 +456,7 @@ int fail(rrt_context* ctx, int code, const char* what, cudaError_t e = cudaSucce
         if (e__ != cudaSuccess) return fail(ctx, RRT_ERR_CUDA, #call, e__);  \
     } while (0)
 
-// Derived constants in float, with the reference's own association (see rrt_device.cuh::Consts).
+// Derived constants in float, with the reference's own association (see include/rrt_device.cuh::Consts).
 Consts make_consts(const rrt_params& P) {
     Consts C;
     std::memset(&C, 0, sizeof(C));

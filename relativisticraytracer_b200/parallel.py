@@ -1,0 +1,104 @@
+"""Multi-GPU sharding of the render path: one process per GPU, torch.distributed for the plumbing.
+
+Every pixel is an independent pure function of (x, y, frame parameters) -- reference raymarch_kernel,
+src/raymarcher.cu:15-174, has no inter-thread communication -- so a frame shards by image rows and a camera
+path shards by frame.  The only exchange step is collecting finished pixels on the encoding GPU (rank 0):
+
+* ``render_banded``: rows are cut into groups of ``group`` consecutive rows, group k goes to rank k % N
+  (cyclic, because contiguous bands are 12-20 % imbalanced: the disk rows are the expensive ones); every rank
+  traces its rows into a packed buffer, one NCCL gather over NVLink brings the N buffers to rank 0, and one
+  small kernel (rrt_assemble_bands) scatters them into the row-flipped frame.  Bit-identical to one GPU.
+* ``frame_owner`` / ``path_frames``: frame k of a path goes to rank k % N (BASELINE config 5).
+
+Host-side index logic lives here in plain Python so it is testable on CPU with the gloo backend.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._capi import OUT_PACKED, Band
+
+DEFAULT_GROUP = 8
+
+
+def band_rows_of(rank: int, nranks: int, group: int, h: int) -> np.ndarray:
+    """Global image rows owned by `rank`, in packed (local-row) order; mirrors the kernel's mapping
+    y = ((l // group) * nranks + rank) * group + l % group."""
+    if not (0 <= rank < nranks) or group <= 0:
+        raise ValueError("bad band")
+    rows = []
+    ngroups = (h + group - 1) // group
+    for g in range(rank, ngroups, nranks):
+        rows.extend(range(g * group, min((g + 1) * group, h)))
+    return np.asarray(rows, dtype=np.int64)
+
+
+def max_band_rows(nranks: int, group: int, h: int) -> int:
+    return max(len(band_rows_of(r, nranks, group, h)) for r in range(nranks))
+
+
+def assemble_host(packed_all: np.ndarray, nranks: int, group: int, h: int) -> np.ndarray:
+    """Host reference of rrt_assemble_bands: packed_all [nranks, rows_max, w, 4] -> row-flipped frame
+    [h, w, 4] (pixel row y is stored at h-1-y, reference raymarcher.cu:168)."""
+    w = packed_all.shape[2]
+    frame = np.zeros((h, w, packed_all.shape[3]), packed_all.dtype)
+    for r in range(nranks):
+        ys = band_rows_of(r, nranks, group, h)
+        frame[h - 1 - ys] = packed_all[r, : len(ys)]
+    return frame
+
+
+def gather_bands(packed: torch.Tensor, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Collect every rank's packed band on `dst`; returns [nranks, rows_max, w, 4] there, None elsewhere.
+    NCCL gather on GPU tensors (NVLink / NVSwitch), gloo on CPU tensors (tests)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if rank == dst:
+        out = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+        dist.gather(packed, list(out.unbind(0)), dst=dst, group=group)
+        return out
+    dist.gather(packed, None, dst=dst, group=group)
+    return None
+
+
+def frame_owner(frame_index: int, nranks: int) -> int:
+    """Frame-parallel path rendering: frame k -> rank k % N."""
+    return frame_index % nranks
+
+
+def path_frames(rank: int, nranks: int, n_frames: int):
+    """Frames (1-based, as the recorder counts them) this rank renders."""
+    return [k for k in range(1, n_frames + 1) if frame_owner(k, nranks) == rank]
+
+
+class BandedFrame:
+    """Buffers + calls for one banded frame on this rank (see module docstring)."""
+
+    def __init__(self, renderer, w: int, h: int, group: int = DEFAULT_GROUP):
+        self.r, self.w, self.h, self.group = renderer, w, h, group
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.band = Band(self.rank, self.world, group)
+        self.rows_max = max_band_rows(self.world, group, h)
+        dev = renderer.device
+        self.packed = torch.zeros((self.rows_max, w, 4), dtype=torch.uint8, device=dev)
+        self.gathered = (torch.zeros((self.world, self.rows_max, w, 4), dtype=torch.uint8, device=dev)
+                         if self.rank == 0 and self.world > 1 else None)
+        self.frame = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev) if self.rank == 0 else None
+
+    def render(self, prm, cam, fx, sky, time: float) -> int:
+        """Trace this rank's rows, gather, assemble on rank 0.  Returns how many of OUR kernels were launched."""
+        if self.world == 1:
+            self.r.render(prm, cam, fx, sky, time, self.w, self.h, out=self.frame)
+            return 1
+        self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.packed, layout=OUT_PACKED)
+        if self.rank == 0:
+            dist.gather(self.packed, list(self.gathered.unbind(0)), dst=0)
+            self.r.assemble_bands(self.gathered, self.rows_max, self.w, self.h, self.world, self.group, frame=self.frame)
+            return 2
+        dist.gather(self.packed, None, dst=0)
+        return 1

@@ -1,5 +1,5 @@
 """The render loop replaces nvcc's guarded IEEE division / square root with their branch-free fast paths
-(csrc/rrt_device.cuh).  This checks, on the device, that they return the correctly rounded result on the
+(include/rrt_device.cuh).  This checks, on the device, that they return the correctly rounded result on the
 operand domain the loop feeds them: 2^31 random pairs, zero tolerance."""
 import pytest
 
