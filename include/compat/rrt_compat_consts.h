@@ -38,6 +38,7 @@ __host__ __device__ inline rrt::Consts consts() {
     C.exposure = EXPOSURE;
     C.max_steps = MAX_STEPS;
     C.flags = 3u;
+    C.neg_zero = -0.0f;
     return C;
 }
 __device__ __forceinline__ rrt::V3 v3(float3 a) { return rrt::mk(a.x, a.y, a.z); }

@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -303,6 +304,269 @@ __global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel(const __
     }
 }
 
+// =====================================================================================================
+// render_kernel2 (opt-in, RRT_KERNEL_VARIANT=2; bit-identical output, same speed as render_kernel on B200 --
+// see profiles/r1_history.md "packed f32x2 experiment"):
+// two rays per thread in packed f32x2 registers (see include/rrt_device.cuh, "Packed FP32").
+// One warp = a 16x4-pixel tile; thread (lx, ly) owns pixels (2*lx, ly) and (2*lx+1, ly) of the tile.  The
+// two rays step in lock-step (same iteration index); a ray that terminates is finalised at once (sky,
+// effects, store) and its half is parked on a harmless far-away state until its partner finishes.
+// =====================================================================================================
+constexpr int kTile2W = 16;
+
+// image-plane coordinate of a pixel after the optional lens distortion (reference :20-25)
+__device__ __forceinline__ void pixel_uv(const FrameArgs& A, int x, int y, float& uvx, float& uvy) {
+    uvx = (float)x / (float)A.w;
+    uvy = (float)y / (float)A.h;
+    if (A.fx.use_lens) {  // post_processing.h:19-24
+        float tu = uvx - 0.5f, tv = uvy - 0.5f;
+        float rr = tu * tu + tv * tv;
+        float f = 1.0f + rr * A.fx.distortion_amount;
+        uvx = tu * f + 0.5f;
+        uvy = tv * f + 0.5f;
+    }
+}
+
+// initial ray of a pixel (reference :27-34)
+__device__ __forceinline__ V3 ray_dir(const FrameArgs& A, int x, int y) {
+    float uvx, uvy;
+    pixel_uv(A, x, y, uvx, uvy);
+    float uc = uvx * 2.0f - 1.0f;
+    float vc = uvy * 2.0f - 1.0f;
+    float aspect = (float)A.w / (float)A.h;
+    uc *= aspect;
+    return rrt::unit3(mk(A.cam.forward[0] + (A.cam.right[0] * uc + A.cam.up[0] * vc),
+                         A.cam.forward[1] + (A.cam.right[1] * uc + A.cam.up[1] * vc),
+                         A.cam.forward[2] + (A.cam.right[2] * uc + A.cam.up[2] * vc)));
+}
+
+constexpr unsigned kEndCaptured = 1u, kEndTouched = 2u, kEndExhausted = 4u;
+
+// Everything after the loop for one ray: background, final assembly, planes, effects, tonemap, store
+// (reference :123-173).  Out of line: runs once per ray, called from three places.
+__device__ __noinline__ void finish_ray(const FrameArgs& A, int x, int y, int ly, float Ir, float Ig, float Ib, float T, V3 p,
+                                        V3 v, int steps, unsigned end) {
+    float bg[3] = {0.f, 0.f, 0.f};
+    V3 d = mk(0.f, 0.f, 0.f);
+    const bool captured = (end & kEndCaptured) != 0;
+    if (!captured) {
+        d = rrt::unit3(v);
+        const float off = A.fx.use_ca ? A.fx.ca_amount : 0.0f;
+        const float theta = asinf(d.y);
+        const float ty_ = 0.5f - theta / rrt::kPi;
+        const float phi0 = atan2f(d.z, d.x);
+        float4 sR = tex2D<float4>(A.sky, 0.5f + (phi0 + off) / (2.0f * rrt::kPi), ty_);
+        float4 sG = tex2D<float4>(A.sky, 0.5f + (phi0 + 0.0f) / (2.0f * rrt::kPi), ty_);
+        float4 sB = tex2D<float4>(A.sky, 0.5f + (phi0 + -off) / (2.0f * rrt::kPi), ty_);
+        bg[0] = sR.x; bg[1] = sG.y; bg[2] = sB.z;
+    }
+    float hr = Ir + bg[0] * T, hg = Ig + bg[1] * T, hb = Ib + bg[2] * T;  // :148-150
+    const bool touched = (end & kEndTouched) != 0, exhausted = (end & kEndExhausted) != 0;
+    const size_t pix = (size_t)y * A.w + x;
+    const uint8_t cls = (uint8_t)((captured ? RRT_CLS_CAPTURED : (touched ? RRT_CLS_DISK_HIT : RRT_CLS_ESCAPED)) |
+                                  (exhausted ? RRT_CLSF_EXHAUSTED : 0u) | (touched ? RRT_CLSF_TOUCHED : 0u));
+    if (A.planes.hdr) reinterpret_cast<float4*>(A.planes.hdr)[pix] = make_float4(hr, hg, hb, T);
+    if (A.planes.dir) reinterpret_cast<float4*>(A.planes.dir)[pix] = make_float4(d.x, d.y, d.z, 0.f);
+    if (A.planes.emis) reinterpret_cast<float4*>(A.planes.emis)[pix] = make_float4(Ir, Ig, Ib, 0.f);
+    if (A.planes.pos) reinterpret_cast<float4*>(A.planes.pos)[pix] = make_float4(p.x, p.y, p.z, 0.f);
+    if (A.planes.vel) reinterpret_cast<float4*>(A.planes.vel)[pix] = make_float4(v.x, v.y, v.z, 0.f);
+    if (A.planes.cls) A.planes.cls[pix] = cls;
+    if (A.planes.steps) A.planes.steps[pix] = steps;
+    if (!A.out) return;
+    if (A.fx.use_bloom) {  // :154-157, post_processing.h:27-31
+        float lum = hr * 0.2126f + hg * 0.7152f + hb * 0.0722f;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (lum > A.fx.bloom_threshold) { b0 = hr; b1 = hg; b2 = hb; }
+        hr = hr + b0 * A.fx.bloom_intensity;
+        hg = hg + b1 * A.fx.bloom_intensity;
+        hb = hb + b2 * A.fx.bloom_intensity;
+    }
+    if (A.fx.use_vignette) {  // :159-161, post_processing.h:13-17
+        float uvx, uvy;
+        pixel_uv(A, x, y, uvx, uvy);
+        float dx = uvx - 0.5f, dy = uvy - 0.5f;
+        float dist = sqrtf(dx * dx + dy * dy + 0.0f);
+        float vg = rrt::sstep(0.8f, 0.2f, dist * A.fx.vignette_intensity);
+        hr *= vg; hg *= vg; hb *= vg;
+    }
+    float o_r = 1.0f - expf(-hr * A.C.exposure);  // :164-166
+    float o_g = 1.0f - expf(-hg * A.C.exposure);
+    float o_b = 1.0f - expf(-hb * A.C.exposure);
+    const uchar4 px = make_uchar4((unsigned char)(o_r * 255), (unsigned char)(o_g * 255), (unsigned char)(o_b * 255), 255);
+    if (A.out_layout == RRT_OUT_FRAME) A.out[(size_t)(A.h - 1 - y) * A.w + x] = px;  // :168
+    else A.out[(size_t)ly * A.w + x] = px;
+}
+
+template <bool SPIN, bool MEDIA>
+__global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel2(const __grid_constant__ FrameArgs A) {
+    using rrt::F2;
+    using rrt::V3x2;
+    const Consts& C = A.C;
+    const int lane = threadIdx.x & 31;
+    const int ntx = (A.w + kTile2W - 1) / kTile2W;
+    const int nty = (A.local_rows + kTileH - 1) / kTileH;
+    const unsigned ntiles = (unsigned)(ntx * nty);
+    const rrt::K2 k2 = rrt::make_k2(C);
+    const F2 kHalf = rrt::bc(0.5f);
+    const int max_steps = C.max_steps;
+    const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
+    const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
+    const V3 cam_p = mk(A.cam.pos[0], A.cam.pos[1], A.cam.pos[2]);
+    const bool fast_ok = rrt::dot3(cam_p, cam_p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
+    const V3 park_p = mk(1000.0f, 0.0f, 0.0f), park_v = mk(0.0f, 0.0f, 0.0f);  // inert state of a finished half
+
+    unsigned long long c_steps = 0, c_disk = 0, c_dust = 0, c_dense = 0;
+    unsigned c_cap = 0, c_esc = 0, c_exh = 0, c_touch = 0;
+
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(A.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        const int tx = (int)(tile % (unsigned)ntx), kk = (int)(tile / (unsigned)ntx);
+        const int cc = nty >> 1, mm = min(cc, nty - 1 - cc);  // centre-out row order, see render_kernel
+        int ty;
+        if (kk <= 2 * mm) ty = (kk & 1) ? cc + ((kk + 1) >> 1) : cc - (kk >> 1);
+        else ty = (cc > nty - 1 - cc) ? (cc - mm - 1) - (kk - (2 * mm + 1)) : (cc + mm + 1) + (kk - (2 * mm + 1));
+        const int x0 = tx * kTile2W + 2 * (lane & 7);
+        const int ly = ty * kTileH + (lane >> 3);
+        int y = 0;
+        bool row_ok = ly < A.local_rows;
+        if (row_ok) {
+            const int grp = ly / A.band_group;
+            y = (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
+            row_ok = y < A.h;
+        }
+        bool alive[2] = {row_ok && x0 < A.w, row_ok && x0 + 1 < A.w};
+        if (!alive[0] && !alive[1]) continue;
+
+        V3x2 P, V;
+        {
+            const V3 vA = alive[0] ? ray_dir(A, x0, y) : park_v, vB = alive[1] ? ray_dir(A, x0 + 1, y) : park_v;
+            const V3 pA = alive[0] ? cam_p : park_p, pB = alive[1] ? cam_p : park_p;
+            P.x = rrt::pk(pA.x, pB.x); P.y = rrt::pk(pA.y, pB.y); P.z = rrt::pk(pA.z, pB.z);
+            V.x = rrt::pk(vA.x, vB.x); V.y = rrt::pk(vA.y, vB.y); V.z = rrt::pk(vA.z, vB.z);
+        }
+        float Ir[2] = {0.f, 0.f}, Ig[2] = {0.f, 0.f}, Ib[2] = {0.f, 0.f}, T[2] = {1.0f, 1.0f};
+        bool touched[2] = {false, false};
+        unsigned n_disk = 0, n_dust = 0, n_dense = 0;
+
+        // retire one half: count it, run the epilogue, park its state
+        auto retire = [&](int hf, int steps, unsigned end, float Tend) {
+            const V3 p = rrt::half_of(P, hf), v = rrt::half_of(V, hf);
+            finish_ray(A, x0 + hf, y, ly, Ir[hf], Ig[hf], Ib[hf], Tend, p, v, steps, end | (touched[hf] ? kEndTouched : 0u));
+            c_steps += (unsigned)steps;
+            c_cap += (end & kEndCaptured) ? 1u : 0u;
+            c_exh += (end & kEndExhausted) ? 1u : 0u;
+            c_esc += (end & (kEndCaptured | kEndExhausted)) ? 0u : 1u;
+            c_touch += touched[hf] ? 1u : 0u;
+            alive[hf] = false;
+            rrt::set_half(P, hf, park_p);
+            rrt::set_half(V, hf, park_v);
+        };
+
+        int it = 0;
+#pragma unroll 1
+        for (; it < max_steps; ++it) {                                                       // :41
+            F2 R2 = rrt::dot2(P, P, k2);
+            F2 R = rrt::sqrt2(R2, k2);                                                       // :44
+            float r[2];
+            rrt::upk(R, r[0], r[1]);
+            bool parked = false;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                if (alive[hf] && r[hf] < C.horizon_r) {                                      // :47-51
+                    retire(hf, it, kEndCaptured, 0.0f);
+                    r[hf] = 1000.0f;
+                    parked = true;
+                }
+            if (!(alive[0] || alive[1])) break;
+            if (parked) {  // radius of the parked half only, so the step below stays in the fast domain
+                float r2l, r2h;
+                rrt::upk(R2, r2l, r2h);
+                R = rrt::pk(r[0], r[1]);
+                R2 = rrt::pk(alive[0] ? r2l : 1.0e6f, alive[1] ? r2h : 1.0e6f);
+            }
+            float h[2], h6[2];
+            unsigned zones[2];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                h[hf] = C.h[0];
+                h6[hf] = C.h6[0];
+                zones[hf] = 0u;
+                if (r[hf] < zone_rmax) {
+                    const float py = rrt::half_of(P.y, hf);
+                    const bool near_bh = r[hf] < 18.0f;                                      // :56
+                    const bool disk_zone = fabsf(py) < C.disk_zone_y && r[hf] < C.disk_zone_r;   // :57
+                    const bool dust_zone = fabsf(py) < C.dust_zone_y && r[hf] < C.dust_zone_r;   // :58
+                    const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));      // :60-62
+                    h[hf] = C.h[zi];
+                    h6[hf] = C.h6[zi];
+                    zones[hf] = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);
+                }
+            }
+            const F2 H = rrt::pk(h[0], h[1]), H6 = rrt::pk(h6[0], h6[1]);
+            const F2 HH = rrt::mul2_raw(H, kHalf);  // exact (power of two)
+            const V3x2 Q = P, Vin = V;          // pre-step state: media and the escape test use Q (:68-69, :120)
+            float rmin[2];
+            rrt::rk4_step2<SPIN>(k2, P, V, H, HH, H6, R2, R, rmin[0], rmin[1]);              // :64
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                if (alive[hf] && (!fast_ok || rmin[hf] < C.acc_rmin)) {  // general-domain redo, see render_kernel
+                    const PV s = rk4_step_general<SPIN>(C, rrt::half_of(Q, hf), rrt::half_of(Vin, hf), h[hf], h[hf] * 0.5f, h6[hf]);
+                    rrt::set_half(P, hf, s.p);
+                    rrt::set_half(V, hf, s.v);
+                }
+            if (MEDIA) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+                    if (alive[hf] && zones[hf]) {                                            // :67
+                        n_disk += zones[hf] & 1u;
+                        n_dust += zones[hf] >> 1;
+                        const MediaOut m = media_sample(C, rrt::half_of(Q, hf), rrt::half_of(V, hf), r[hf], h[hf], A.time, zones[hf]);
+                        if (m.dense) {                                                       // :71
+                            touched[hf] = true;
+                            ++n_dense;
+                            const float wgt = (1.0f - m.s) * T[hf];                          // :109
+                            Ir[hf] += m.er * wgt; Ig[hf] += m.eg * wgt; Ib[hf] += m.eb * wgt;    // :111-113
+                            T[hf] *= m.s;                                                    // :115
+                        }
+                    }
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                if (alive[hf] && r[hf] > 250.0f && rrt::dot3(rrt::half_of(Q, hf), rrt::half_of(V, hf)) > 0.0f)   // :120
+                    retire(hf, it + 1, 0u, T[hf]);
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+            if (alive[hf]) retire(hf, it, kEndExhausted, T[hf]);  // the loop ran out (:41)
+        c_disk += n_disk; c_dust += n_dust; c_dense += n_dense;
+    }
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_steps += __shfl_xor_sync(0xffffffffu, c_steps, o);
+        c_disk += __shfl_xor_sync(0xffffffffu, c_disk, o);
+        c_dust += __shfl_xor_sync(0xffffffffu, c_dust, o);
+        c_dense += __shfl_xor_sync(0xffffffffu, c_dense, o);
+        c_cap += __shfl_xor_sync(0xffffffffu, c_cap, o);
+        c_esc += __shfl_xor_sync(0xffffffffu, c_esc, o);
+        c_exh += __shfl_xor_sync(0xffffffffu, c_exh, o);
+        c_touch += __shfl_xor_sync(0xffffffffu, c_touch, o);
+    }
+    if (lane == 0 && A.counters) {
+        atomicAdd(A.counters + 0, c_steps);
+        atomicAdd(A.counters + 1, c_disk);
+        atomicAdd(A.counters + 2, c_dust);
+        atomicAdd(A.counters + 3, c_dense);
+        atomicAdd(A.counters + 4, (unsigned long long)c_cap);
+        atomicAdd(A.counters + 5, (unsigned long long)c_esc);
+        atomicAdd(A.counters + 6, (unsigned long long)c_exh);
+        atomicAdd(A.counters + 7, (unsigned long long)c_touch);
+    }
+}
+
 // ---- band assembly on the encoding GPU ------------------------------------------------------------
 __global__ void assemble_kernel(const uchar4* __restrict__ packed, int rows_per_rank, int w, int h, int nranks,
                                 int group, uchar4* __restrict__ frame) {
@@ -429,6 +693,7 @@ struct rrt_context {
     unsigned long long* d_counters = nullptr;
     unsigned int* d_tickets = nullptr;
     unsigned ticket_next = 0;
+    int kernel_variant = 1;  // RRT_KERNEL_VARIANT=2 selects the packed two-rays-per-thread kernel (A/B runs)
     void* d_frame = nullptr;
     size_t d_frame_bytes = 0;
     std::string err;
@@ -498,6 +763,7 @@ Consts make_consts(const rrt_params& P) {
     C.exposure = P.exposure;
     C.max_steps = P.max_steps;
     C.flags = P.flags;
+    C.neg_zero = -0.0f;
     return C;
 }
 
@@ -551,6 +817,7 @@ int rrt_context_create(int device, rrt_context** out) {
     if (!ctx) return fail(nullptr, RRT_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* kv = std::getenv("RRT_KERNEL_VARIANT")) ctx->kernel_variant = std::atoi(kv) == 2 ? 2 : 1;
     DevGuard g(device);
     if ((e = cudaMalloc(&ctx->d_counters, sizeof(rrt_counters))) != cudaSuccess ||
         (e = cudaMemset(ctx->d_counters, 0, sizeof(rrt_counters))) != cudaSuccess ||
@@ -700,12 +967,17 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
 
     const bool spin = prm->spin_a != 0.0f;
     const bool media = (prm->flags & (RRT_FLAG_DISK | RRT_FLAG_DUST)) != 0;
-    void (*kern)(const FrameArgs) = spin ? (media ? render_kernel<true, true> : render_kernel<true, false>)
-                                         : (media ? render_kernel<false, true> : render_kernel<false, false>);
+    const bool packed = ctx->kernel_variant == 2;  // 1 (default): one ray per thread; 2: two rays per thread in f32x2 registers
+    void (*kern)(const FrameArgs);
+    if (packed) kern = spin ? (media ? render_kernel2<true, true> : render_kernel2<true, false>)
+                            : (media ? render_kernel2<false, true> : render_kernel2<false, false>);
+    else kern = spin ? (media ? render_kernel<true, true> : render_kernel<true, false>)
+                     : (media ? render_kernel<false, true> : render_kernel<false, false>);
     int per_sm = 0;
     RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
     if (per_sm < 1) per_sm = 1;
-    const long long ntiles = (long long)((w + kTileW - 1) / kTileW) * ((local_rows + kTileH - 1) / kTileH);
+    const int tile_w = packed ? kTile2W : kTileW;
+    const long long ntiles = (long long)((w + tile_w - 1) / tile_w) * ((local_rows + kTileH - 1) / kTileH);
     long long grid = (long long)ctx->sm_count * per_sm;
     const long long need = (ntiles + (kBlock / 32) - 1) / (kBlock / 32);
     if (grid > need) grid = need;
