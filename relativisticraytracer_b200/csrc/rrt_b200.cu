@@ -78,10 +78,9 @@ struct MediaOut {
     float er, eg, eb, s;
     int dense;
 };
-__device__ __noinline__ MediaOut media_sample(const Consts& C, V3 q, V3 v, float r, float h, float time, unsigned zones) {
+// Emission colour and step transmittance of one sample given both densities (reference :71-108).
+__device__ __noinline__ MediaOut media_final(const Consts& C, V3 q, V3 v, float r, float h, float dd, float dc) {
     MediaOut o = {0.f, 0.f, 0.f, 1.0f, 0};
-    const float dd = (zones & 1u) ? rrt::disk_density(C, q, time) : 0.0f;                 // :68
-    const float dc = (zones & 2u) ? rrt::dust_density(C, q, time) : 0.0f;                 // :69
     if (dd > 0.001f || dc > 0.001f) {                                                     // :71
         o.dense = 1;
         float er = 0.f, eg = 0.f, eb = 0.f, kappa = 0.f;
@@ -110,6 +109,11 @@ __device__ __noinline__ MediaOut media_sample(const Consts& C, V3 q, V3 v, float
         o.er = er; o.eg = eg; o.eb = eb;
     }
     return o;
+}
+__device__ __forceinline__ MediaOut media_sample(const Consts& C, V3 q, V3 v, float r, float h, float time, unsigned zones) {
+    const float dd = (zones & 1u) ? rrt::disk_density(C, q, time) : 0.0f;                 // :68
+    const float dc = (zones & 2u) ? rrt::dust_density(C, q, time) : 0.0f;                 // :69
+    return media_final(C, q, v, r, h, dd, dc);
 }
 
 // One ray: reference raymarch_kernel lines 20-150.
@@ -567,6 +571,319 @@ __global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel2(const _
     }
 }
 
+// =====================================================================================================
+// render_kernel3 (opt-in, RRT_KERNEL_VARIANT=3; bit-identical output, slower than render_kernel at N=1 -- see
+// profiles/r1_history.md "wavefront-in-a-warp experiment"): a wavefront inside every persistent warp.
+//
+// What limits render_kernel on B200 is not the vacuum step (straight-line FMA code, all lanes busy) but the
+// side work: media samples evaluated under per-lane branches, and the fact that one 8x4 tile of disk-plane
+// rays is ~5e6 warp-instructions of sequential work, which is what a band-parallel 8-GPU frame ends up
+// waiting for.  Here:
+//   * every lane owns one ray and is refilled individually from a global ticket when its ray ends
+//     (persistent threads with lane refill).  Tickets are 4-pixel strips and 8 consecutive strips come from
+//     8 distant parts of the centre-out ordered frame, so the expensive disk-plane rays are spread four to
+//     a warp instead of 32 to a warp;
+//   * a lane that is inside a medium does not evaluate it: it appends a SAMPLE JOB (pre-step position,
+//     post-step velocity, zone bits, step-size index, owner lane) to a per-warp ring in shared memory and
+//     keeps stepping.  Every kBurst iterations the warp pumps the ring through three stages, each run with
+//     one job per lane as soon as 32 jobs are waiting for it:
+//        1. disk density + dust envelope of 32 consecutive jobs (survivors of the envelope test are listed),
+//        2. the domain-warped ridge noise of 32 listed dust jobs,
+//        3. redshift / emission / exp(-tau) of 32 consecutive completed jobs, after which every owner lane
+//           folds the results of ITS jobs into its (I, T) registers in ring order.
+//     The ring is FIFO and a ray's jobs are appended in step order, so each ray sees exactly the
+//     reference's sequence of I += e(1-s)T; T *= s updates (raymarcher.cu:107-115): results are
+//     bit-identical to render_kernel;
+//   * a ray that ends with jobs still in the ring forces a drain first; the capture rule T = 0
+//     (raymarcher.cu:49) is applied when the ray is finalised, after its queued emission has been added with
+//     the running T.
+// =====================================================================================================
+constexpr int kStripW = 4;       // pixels per ticket strip
+constexpr int kInterleave = 8;   // consecutive strips are taken from this many distant parts of the frame
+constexpr int kRing = 256;       // sample-job slots per warp (power of two)
+constexpr int kBurst = 2;        // loop iterations between two control points
+constexpr int kRetireMin = 4;    // finished lanes wait until this many can be finalised + refilled together
+
+struct WarpQueue {
+    float qx[kRing], qy[kRing], qz[kRing], vx[kRing], vy[kRing], vz[kRing];
+    float dd[kRing], dc[kRing];   // densities, filled by stages 1 and 2 (dc holds the dust envelope in between)
+    unsigned meta[kRing];         // owner lane | zones << 5 | step-size index << 7
+    unsigned dlist[kRing];        // ring of job sequence numbers waiting for stage 2
+    float er[32], eg[32], eb[32], s[32];  // stage-3 results of the batch being folded
+    unsigned tail;                // sequence number of the next job
+};
+
+// ticket -> pixel.  Tickets count pixels of 4x1 strips; strip s is strip (s % 8) * part + s / 8 of the base order,
+// the base order being rows from the band centre outwards (see render_kernel), left to right.
+__device__ __forceinline__ bool ticket_pixel(const FrameArgs& A, unsigned idx, int spr, unsigned nstrips, unsigned part, int& x,
+                                             int& ly) {
+    const unsigned s = idx / kStripW, l = idx - s * kStripW;
+    const unsigned j = s % kInterleave, b = j * part + s / kInterleave;
+    if (b >= nstrips) return false;
+    const int k = (int)(b / (unsigned)spr), sx = (int)(b - (unsigned)k * (unsigned)spr);
+    const int rows = A.local_rows, c = rows >> 1, m = min(c, rows - 1 - c);
+    if (k <= 2 * m) ly = (k & 1) ? c + ((k + 1) >> 1) : c - (k >> 1);
+    else ly = (c > rows - 1 - c) ? (c - m - 1) - (k - (2 * m + 1)) : (c + m + 1) + (k - (2 * m + 1));
+    x = sx * kStripW + (int)l;
+    return x < A.w;
+}
+__device__ __forceinline__ int band_row(const FrameArgs& A, int ly) {
+    const int grp = ly / A.band_group;
+    return (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
+}
+
+template <bool SPIN, bool MEDIA>
+__global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel3(const __grid_constant__ FrameArgs A) {
+    __shared__ WarpQueue s_queue[MEDIA ? kBlock / 32 : 1];
+    WarpQueue& Q = s_queue[MEDIA ? (threadIdx.x >> 5) : 0];
+    const Consts& C = A.C;
+    const unsigned FULL = 0xffffffffu, RM = kRing - 1;
+    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+    const int spr = (A.w + kStripW - 1) / kStripW;
+    const unsigned nstrips = (unsigned)spr * (unsigned)A.local_rows;
+    const unsigned part = (nstrips + kInterleave - 1) / kInterleave;
+    const unsigned total = part * kInterleave * kStripW;
+    const int max_steps = C.max_steps;
+    const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
+    const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
+    const V3 cam_p = mk(A.cam.pos[0], A.cam.pos[1], A.cam.pos[2]);
+    const bool fast_ok = rrt::dot3(cam_p, cam_p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
+
+    unsigned long long c_steps = 0;
+    unsigned c_disk = 0, c_dust = 0, c_dense = 0, c_cap = 0, c_esc = 0, c_exh = 0, c_touch = 0;
+
+    enum : int { kEmpty = 0, kActive = 1, kDone = 2 };
+    int st = kEmpty;
+    unsigned end = 0;      // kEnd* bits of the current ray
+    unsigned npend = 0;    // this lane's jobs not yet folded
+    V3 p = cam_p, v = mk(0.f, 0.f, 0.f);
+    float Ir = 0.f, Ig = 0.f, Ib = 0.f, T = 1.0f;
+    int it = 0, x = 0, ly = 0;
+    // warp-uniform ring state (sequence numbers; slot = seq & RM):  head <= s1 <= tail
+    unsigned head = 0;     // oldest job not yet folded
+    unsigned s1 = 0;       // next job for stage 1
+    unsigned dhead = 0, dtail = 0;  // stage-2 list
+    unsigned wit = 0;      // control points seen
+    bool tickets_left = true;
+    if (MEDIA) {
+        if (lane == 0) Q.tail = 0u;
+        __syncwarp();
+    }
+
+    // Run every stage that has a full batch; with drain = true run them until the ring is empty.
+    auto pump = [&](bool drain) {
+        __syncwarp();
+        const unsigned tail = *(volatile unsigned*)&Q.tail;
+        // ---- stage 1: disk density (:68) and dust envelope (densities.h:70-84) ----
+        while (tail - s1 >= 32u || (drain && tail != s1)) {
+            const unsigned n = min(32u, tail - s1);
+            bool need = false;
+            unsigned seq = s1 + lane;
+            if (lane < n) {
+                const unsigned sl = seq & RM, m = Q.meta[sl];
+                const V3 jq = mk(Q.qx[sl], Q.qy[sl], Q.qz[sl]);
+                Q.dd[sl] = (m & 32u) ? rrt::disk_density(C, jq, A.time) : 0.0f;
+                const float base = (m & 64u) ? rrt::dust_base(C, jq) : 0.0f;
+                Q.dc[sl] = base;
+                need = base != 0.0f;
+            }
+            const unsigned nm = __ballot_sync(FULL, need);
+            if (need) Q.dlist[(dtail + (unsigned)__popc(nm & lt_mask)) & RM] = seq;
+            dtail += (unsigned)__popc(nm);
+            s1 += n;
+            __syncwarp();
+        }
+        // ---- stage 2: dust strands (densities.h:86-131) ----
+        while (dtail - dhead >= 32u || (drain && dtail != dhead)) {
+            const unsigned n = min(32u, dtail - dhead);
+            if (lane < n) {
+                const unsigned sl = Q.dlist[(dhead + lane) & RM] & RM;
+                const V3 jq = mk(Q.qx[sl], Q.qy[sl], Q.qz[sl]);
+                Q.dc[sl] = rrt::dust_strands(C, jq, A.time, Q.dc[sl]);                        // :69
+            }
+            dhead += n;
+            __syncwarp();
+        }
+        // ---- stage 3: transfer of completed jobs, in ring order ----
+        const unsigned ready = (dhead == dtail) ? s1 : Q.dlist[dhead & RM];  // first job still waiting for stage 2
+        while (ready - head >= 32u || (drain && ready != head)) {
+            const unsigned n = min(32u, ready - head);
+            const bool have = lane < n;
+            unsigned owner = 0;
+            bool dense = false;
+            if (have) {
+                const unsigned sl = (head + lane) & RM, m = Q.meta[sl];
+                owner = m & 31u;
+                const V3 jq = mk(Q.qx[sl], Q.qy[sl], Q.qz[sl]);
+                const V3 jv = mk(Q.vx[sl], Q.vy[sl], Q.vz[sl]);
+                const float jr = rrt::sqrt_rn_fast(rrt::dot3(jq, jq));  // the loop header's r of that step (:43-44)
+                const unsigned zi = m >> 7;
+                const float jh = zi == 1u ? C.h[1] : (zi == 2u ? C.h[2] : (zi == 3u ? C.h[3] : C.h[0]));
+                const MediaOut o = media_final(C, jq, jv, jr, jh, Q.dd[sl], Q.dc[sl]);
+                dense = o.dense != 0;
+                Q.er[lane] = o.er; Q.eg[lane] = o.eg; Q.eb[lane] = o.eb; Q.s[lane] = o.s;
+            }
+            const unsigned dense_m = __ballot_sync(FULL, dense);
+            unsigned mine = n >= 32u ? FULL : ((1u << n) - 1u);  // becomes: batch entries owned by this lane
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const unsigned bk = __ballot_sync(FULL, have && ((owner >> k) & 1u));
+                mine &= ((lane >> k) & 1u) ? bk : ~bk;
+            }
+            __syncwarp();
+            npend -= (unsigned)__popc(mine);
+            mine &= dense_m;                                                                  // :71
+            while (mine) {
+                const int j = __ffs((int)mine) - 1;
+                mine &= mine - 1u;
+                const float s = Q.s[j];
+                const float wgt = (1.0f - s) * T;                                             // :109
+                Ir += Q.er[j] * wgt; Ig += Q.eg[j] * wgt; Ib += Q.eb[j] * wgt;                // :111-113
+                T *= s;                                                                       // :115
+                end |= kEndTouched;
+                ++c_dense;
+            }
+            head += n;
+            __syncwarp();
+        }
+    };
+
+    for (;;) {
+        // ---- control point: finalise finished rays, refill empty lanes ----
+        const unsigned act_m = __ballot_sync(FULL, st == kActive);
+        const unsigned done_m = __ballot_sync(FULL, st == kDone);
+        if (act_m == 0u || (done_m != 0u && (__popc(done_m) >= kRetireMin || (wit & 15u) == 0u))) {
+            if (done_m) {
+                if (MEDIA && __any_sync(FULL, st == kDone && npend != 0u)) pump(true);
+                if (st == kDone) {                                                            // reference :123-173
+                    const bool captured = (end & kEndCaptured) != 0;
+                    finish_ray(A, x, band_row(A, ly), ly, Ir, Ig, Ib, captured ? 0.0f : T, p, v, it, end);   // T = 0: :49
+                    c_steps += (unsigned)it;
+                    c_cap += captured ? 1u : 0u;
+                    c_exh += (end & kEndExhausted) ? 1u : 0u;
+                    c_esc += (end & (kEndCaptured | kEndExhausted)) ? 0u : 1u;
+                    c_touch += (end & kEndTouched) ? 1u : 0u;
+                    st = kEmpty;
+                }
+            }
+            if (tickets_left) {
+                const unsigned empty_m = __ballot_sync(FULL, st == kEmpty);
+                const unsigned n = (unsigned)__popc(empty_m);
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(A.ticket, n);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + n >= total) tickets_left = false;
+                if (st == kEmpty) {
+                    const unsigned idx = base + (unsigned)__popc(empty_m & lt_mask);
+                    if (idx < total && ticket_pixel(A, idx, spr, nstrips, part, x, ly)) {
+                        p = cam_p;
+                        v = ray_dir(A, x, band_row(A, ly));                                   // :20-34
+                        Ir = 0.f; Ig = 0.f; Ib = 0.f; T = 1.0f;                               // :36-38
+                        it = 0;
+                        end = max_steps > 0 ? 0u : kEndExhausted;
+                        st = max_steps > 0 ? kActive : kDone;
+                    }
+                }
+            }
+            if (!__any_sync(FULL, st != kEmpty)) {
+                if (!tickets_left) break;
+                continue;
+            }
+        }
+        ++wit;
+
+        // ---- kBurst loop iterations of reference :41-121 for every active lane, no warp-wide operation inside ----
+#pragma unroll 1
+        for (int b = 0; b < kBurst; ++b) {
+            if (st == kActive) {
+                const float r2 = rrt::dot3(p, p);
+                const float r = rrt::sqrt_rn_fast(r2);                                        // :44
+                if (r < C.horizon_r) {                                                        // :47-51
+                    st = kDone;
+                    end |= kEndCaptured;
+                } else {
+                    bool disk_zone = false, dust_zone = false;
+                    int zi = 0;
+                    float h = C.h[0], h6 = C.h6[0];
+                    if (r < zone_rmax) {
+                        const bool near_bh = r < 18.0f;                                       // :56
+                        disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;          // :57
+                        dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;          // :58
+                        zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));             // :60-62
+                        // selects between uniform constants, not an indexed constant load: lanes of one warp are in
+                        // different zones here and a divergent c[][] index is replayed per distinct address
+                        h = near_bh ? C.h[1] : (disk_zone ? C.h[2] : (dust_zone ? C.h[3] : C.h[0]));
+                        h6 = near_bh ? C.h6[1] : (disk_zone ? C.h6[2] : (dust_zone ? C.h6[3] : C.h6[0]));
+                    }
+                    const float hh = h * 0.5f;  // exact
+                    const V3 q = p, v_in = v;
+                    const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);   // :64
+                    if (!fast_ok || rmin < C.acc_rmin) {  // general-domain redo, see render_kernel
+                        const PV sres = rk4_step_general<SPIN>(C, q, v_in, h, hh, h6);
+                        p = sres.p; v = sres.v;
+                    }
+                    ++it;
+                    if (MEDIA && (disk_zone || dust_zone)) {                                  // :67
+                        const unsigned zones = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);
+                        c_disk += zones & 1u;
+                        c_dust += zones >> 1;
+                        if (zones) {
+                            // both density functions return 0 outside ISCO <= R <= DISK_OUT (densities.h:21-23,
+                            // 70-72): only samples inside that ring become jobs
+                            const float R = rrt::sqrt_rn_fast(q.x * q.x + 0.0f * 0.0f + q.z * q.z);
+                            if (R >= C.isco && R <= C.disk_out) {
+                                // warp-aggregated append: one shared-memory atomic per converged group of lanes
+                                const unsigned am = __activemask();
+                                const int leader = __ffs((int)am) - 1;
+                                unsigned seq = 0;
+                                if ((int)lane == leader) seq = atomicAdd(&Q.tail, (unsigned)__popc(am));
+                                seq = __shfl_sync(am, seq, leader) + (unsigned)__popc(am & lt_mask);
+                                const unsigned sl = seq & RM;
+                                Q.qx[sl] = q.x; Q.qy[sl] = q.y; Q.qz[sl] = q.z;
+                                Q.vx[sl] = v.x; Q.vy[sl] = v.y; Q.vz[sl] = v.z;               // post-step velocity (:77)
+                                Q.meta[sl] = lane | (zones << 5) | ((unsigned)zi << 7);
+                                ++npend;
+                            }
+                        }
+                    }
+                    if (r > 250.0f && rrt::dot3(q, v) > 0.0f) st = kDone;                     // :120
+                    else if (it >= max_steps) { st = kDone; end |= kEndExhausted; }           // :41
+                }
+            }
+        }
+        if (MEDIA) {
+            __syncwarp();
+            const unsigned tail = *(volatile unsigned*)&Q.tail;
+            if (tail - s1 >= 32u) pump(false);
+            if (tail - head > (unsigned)(kRing - 32 * kBurst)) pump(true);  // no room for another burst: drain
+        }
+    }
+
+    // one set of atomics per warp
+    unsigned long long w_disk = c_disk, w_dust = c_dust, w_dense = c_dense;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_steps += __shfl_xor_sync(FULL, c_steps, o);
+        w_disk += __shfl_xor_sync(FULL, w_disk, o);
+        w_dust += __shfl_xor_sync(FULL, w_dust, o);
+        w_dense += __shfl_xor_sync(FULL, w_dense, o);
+        c_cap += __shfl_xor_sync(FULL, c_cap, o);
+        c_esc += __shfl_xor_sync(FULL, c_esc, o);
+        c_exh += __shfl_xor_sync(FULL, c_exh, o);
+        c_touch += __shfl_xor_sync(FULL, c_touch, o);
+    }
+    if (lane == 0 && A.counters) {
+        atomicAdd(A.counters + 0, c_steps);
+        atomicAdd(A.counters + 1, w_disk);
+        atomicAdd(A.counters + 2, w_dust);
+        atomicAdd(A.counters + 3, w_dense);
+        atomicAdd(A.counters + 4, (unsigned long long)c_cap);
+        atomicAdd(A.counters + 5, (unsigned long long)c_esc);
+        atomicAdd(A.counters + 6, (unsigned long long)c_exh);
+        atomicAdd(A.counters + 7, (unsigned long long)c_touch);
+    }
+}
+
 // ---- band assembly on the encoding GPU ------------------------------------------------------------
 __global__ void assemble_kernel(const uchar4* __restrict__ packed, int rows_per_rank, int w, int h, int nranks,
                                 int group, uchar4* __restrict__ frame) {
@@ -693,7 +1010,7 @@ struct rrt_context {
     unsigned long long* d_counters = nullptr;
     unsigned int* d_tickets = nullptr;
     unsigned ticket_next = 0;
-    int kernel_variant = 1;  // RRT_KERNEL_VARIANT=2 selects the packed two-rays-per-thread kernel (A/B runs)
+    int kernel_variant = 1;  // RRT_KERNEL_VARIANT: 1 tile-per-warp (default), 2 packed f32x2, 3 wavefront-in-warp (measured alternatives)
     void* d_frame = nullptr;
     size_t d_frame_bytes = 0;
     std::string err;
@@ -817,7 +1134,10 @@ int rrt_context_create(int device, rrt_context** out) {
     if (!ctx) return fail(nullptr, RRT_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* kv = std::getenv("RRT_KERNEL_VARIANT")) ctx->kernel_variant = std::atoi(kv) == 2 ? 2 : 1;
+    if (const char* kv = std::getenv("RRT_KERNEL_VARIANT")) {
+        const int k = std::atoi(kv);
+        if (k >= 1 && k <= 3) ctx->kernel_variant = k;
+    }
     DevGuard g(device);
     if ((e = cudaMalloc(&ctx->d_counters, sizeof(rrt_counters))) != cudaSuccess ||
         (e = cudaMemset(ctx->d_counters, 0, sizeof(rrt_counters))) != cudaSuccess ||
@@ -967,19 +1287,23 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
 
     const bool spin = prm->spin_a != 0.0f;
     const bool media = (prm->flags & (RRT_FLAG_DISK | RRT_FLAG_DUST)) != 0;
-    const bool packed = ctx->kernel_variant == 2;  // 1 (default): one ray per thread; 2: two rays per thread in f32x2 registers
+    const int variant = ctx->kernel_variant;  // 1 (default): one tile per warp; 2: two rays per thread (f32x2); 3: wavefront in a warp
     void (*kern)(const FrameArgs);
-    if (packed) kern = spin ? (media ? render_kernel2<true, true> : render_kernel2<true, false>)
-                            : (media ? render_kernel2<false, true> : render_kernel2<false, false>);
-    else kern = spin ? (media ? render_kernel<true, true> : render_kernel<true, false>)
-                     : (media ? render_kernel<false, true> : render_kernel<false, false>);
+    if (variant == 2) kern = spin ? (media ? render_kernel2<true, true> : render_kernel2<true, false>)
+                                  : (media ? render_kernel2<false, true> : render_kernel2<false, false>);
+    else if (variant == 1) kern = spin ? (media ? render_kernel<true, true> : render_kernel<true, false>)
+                                       : (media ? render_kernel<false, true> : render_kernel<false, false>);
+    else kern = spin ? (media ? render_kernel3<true, true> : render_kernel3<true, false>)
+                     : (media ? render_kernel3<false, true> : render_kernel3<false, false>);
+    if ((long long)w * local_rows > (1ll << 30)) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render: band larger than 2^30 pixels");
+    // the job rings of render_kernel3 want the large shared-memory carve-out (43 KB per CTA, 5 CTAs per SM)
+    RRT_CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
     if (per_sm < 1) per_sm = 1;
-    const int tile_w = packed ? kTile2W : kTileW;
-    const long long ntiles = (long long)((w + tile_w - 1) / tile_w) * ((local_rows + kTileH - 1) / kTileH);
+    const long long rays_per_block = (variant == 2 ? 2 : 1) * (long long)kBlock;
     long long grid = (long long)ctx->sm_count * per_sm;
-    const long long need = (ntiles + (kBlock / 32) - 1) / (kBlock / 32);
+    const long long need = ((long long)w * local_rows + rays_per_block - 1) / rays_per_block;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, kBlock, 0, st>>>(A);
     RRT_CU(ctx, cudaGetLastError());
