@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--flags", type=int, default=3, help="experiment only: media flags (3 = disk+dust = the headline workload)")
     ap.add_argument("--camera", default="C0", help="experiment only: C0 (headline) .. C3")
+    ap.add_argument("--depth", type=int, default=2, help="frames in flight in the timed sequence (1 = one at a time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     return ap.parse_args()
@@ -241,8 +242,34 @@ def main():
             kernel_ms += e0.elapsed_time(e1)
         return total_ms, kernel_ms, launches
 
+    from relativisticraytracer_b200.parallel import FramePipeline
+    depth = max(1, min(args.depth, 4))
+    pipe_dev = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=False)
+    pipe_host = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=True)
+
+    def timed_sequence(pipe, n_steps: int):
+        """K frames as a sequence with `depth` frames in flight (frame k on stream k % depth), the whole
+        sequence bracketed by barrier + synchronize.  Returns (device ms by CUDA events, host wall ms, launches)."""
+        launches = 0
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        pipe.begin()
+        for k in range(n_steps):
+            with torch.cuda.stream(pipe.streams[pipe.submitted % pipe.depth]):
+                flush.fill_(1)                                   # L2 flushed before every frame, in that frame's stream
+            launches += pipe.submit(prm, cam, fx, sky, TIME)
+        pipe.end()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        return e0.elapsed_time(e1), wall_ms, launches
+
     # ---- warm-up, then the counted work of one step -------------------------------------------------
     timed(args.warmup, False)
+    timed_sequence(pipe_dev, min(args.warmup, depth))
     r.read_counters(reset=True)
     one_frame(False)
     torch.cuda.synchronize()
@@ -252,22 +279,23 @@ def main():
         dist.all_reduce(steps_local)
     rk4_per_frame, disk_evals, dust_evals = (float(x) for x in steps_local.tolist())
 
-    # ---- timed region: device-resident ---------------------------------------------------------------
+    # ---- single-frame latency and the kernel's own duration (each frame alone, bracketed) ----------------
+    lat_ms, kern_ms, _ = timed(args.steps, False)
+    # ---- timed region: K frames, device-resident, `depth` in flight -------------------------------------
     with ClockSampler(dev) as clk:
-        barrier()
-        tot_ms, kern_ms, launches = timed(args.steps, False)
-        barrier()
-    # ---- timed region: end to end (host destination) ---------------------------------------------------
-    timed(1, True)
-    e2e_ms, _, _ = timed(args.steps, True)
+        tot_ms, _, launches = timed_sequence(pipe_dev, args.steps)
+    # ---- timed region: end to end (HOST destination, device->host copy inside) --------------------------
+    timed_sequence(pipe_host, min(2, args.steps))
+    _, e2e_ms, _ = timed_sequence(pipe_host, args.steps)
 
-    t = torch.tensor([tot_ms, kern_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([tot_ms, kern_ms, e2e_ms, lat_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot_ms, kern_ms, e2e_ms = (float(x) for x in t.tolist())
+    tot_ms, kern_ms, e2e_ms, lat_ms = (float(x) for x in t.tolist())
     ms_per_step = tot_ms / args.steps
     kern_ms_per_step = kern_ms / args.steps
     e2e_ms_per_step = e2e_ms / args.steps
+    lat_ms_per_step = lat_ms / args.steps
     value = rk4_per_frame / (ms_per_step * 1e-3)
 
     if rank != 0:
@@ -294,14 +322,17 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD if (w, h, args.flags, args.camera) == (W4K, H4K, 3, "C0") else f"EXPERIMENT {w}x{h} flags={args.flags} camera={args.camera} variant of: {WORKLOAD}",
                    "width": w, "height": h, "spin_a": SPIN, "media": "disk+dust", "camera": "C0", "band_group_rows": BAND_GROUP,
-                   "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) between timed steps",
+                   "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) before every frame",
+                   "frames_in_flight": depth,
                    "rk4_steps_per_frame": rk4_per_frame, "disk_evals_per_frame": disk_evals, "dust_evals_per_frame": dust_evals},
         "frames_per_s": 1e3 / ms_per_step,
+        "latency_ms_single_frame": lat_ms_per_step,
         "roofline": roofline,
         "e2e": {"value": rk4_per_frame / (e2e_ms_per_step * 1e-3), "unit": "steps/s",
                 "frames_per_s": 1e3 / e2e_ms_per_step, "ms_per_step": e2e_ms_per_step,
                 "h2d_bytes_per_step": 64 + 48 + 36 + 16, "d2h_bytes_per_step": w * h * 4,
-                "path": "rrt_render_host (C ABI, pinned host frame)" if world == 1 else "rrt_render per rank + NCCL gather + rrt_assemble_bands + D2H"},
+                "timing": "host wall clock around the K-frame sequence incl. final synchronize",
+                "path": "rrt_render_host_async (C ABI, pinned host frames)" if world == 1 else "rrt_render per rank + NCCL gather + rrt_assemble_bands + D2H to pinned host"},
         "gpu_launches": launches,
         "clocks": clk.summary(),
     }

@@ -143,6 +143,16 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
 int rrt_render_host(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
                     uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba);
 
+/* The same without the final synchronisation, for frame sequences (the recorder loop of src/main.cpp:505-528
+ * renders frame after frame): enqueues the trace and the device->host copy on `stream` and returns.  `slot`
+ * (0 .. RRT_HOST_SLOTS-1) picks the context-owned device frame, so that up to RRT_HOST_SLOTS frames can be in
+ * flight on different streams; a slot may be reused once the work previously enqueued with it has completed
+ * (stream order guarantees that when a slot is always used with the same stream).  host_rgba should be pinned
+ * memory, otherwise the copy is staged and synchronous. */
+#define RRT_HOST_SLOTS 4
+int rrt_render_host_async(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
+                          uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba, int slot, void* stream);
+
 /* Number of rows a band owns in an h-row image (packed buffer height). */
 int rrt_band_rows(const rrt_band* band, int h);
 

@@ -17,6 +17,7 @@ FLAG_DISK, FLAG_DUST = 1, 2
 CLS_CAPTURED, CLS_DISK_HIT, CLS_ESCAPED, CLS_MASK = 0, 1, 2, 3
 CLSF_EXHAUSTED, CLSF_TOUCHED = 4, 8
 OUT_FRAME, OUT_PACKED = 0, 1
+HOST_SLOTS = 4   # RRT_HOST_SLOTS
 
 
 class RrtError(RuntimeError):
@@ -67,7 +68,7 @@ class Counters(C.Structure):
 SYMBOLS = [
     "rrt_abi_version", "rrt_build_info", "rrt_context_create", "rrt_context_destroy", "rrt_last_error",
     "rrt_default_params", "rrt_default_effects", "rrt_sky_create", "rrt_sky_texture", "rrt_sky_destroy",
-    "rrt_render", "rrt_render_host", "rrt_band_rows", "rrt_assemble_bands", "rrt_read_counters",
+    "rrt_render", "rrt_render_host", "rrt_render_host_async", "rrt_band_rows", "rrt_assemble_bands", "rrt_read_counters",
     "rrt_geodesic_acc_batch", "rrt_rk4_step_batch", "rrt_euler_step_batch", "rrt_redshift_batch",
     "rrt_hash31_batch", "rrt_noise3d_batch", "rrt_fbm_batch", "rrt_disk_temperature_batch",
     "rrt_disk_density_batch", "rrt_dust_density_batch", "rrt_sky_sample_batch", "rrt_fp32_peak_probe",
@@ -108,6 +109,7 @@ def load() -> C.CDLL:
     lib.rrt_render.argtypes = [vp, P(Params), P(Camera), P(Effects), C.c_uint64, cf, ci, ci, P(Band), vp, ci,
                                P(Planes), vp]
     lib.rrt_render_host.argtypes = [vp, P(Params), P(Camera), P(Effects), C.c_uint64, cf, ci, ci, vp]
+    lib.rrt_render_host_async.argtypes = [vp, P(Params), P(Camera), P(Effects), C.c_uint64, cf, ci, ci, vp, ci, vp]
     lib.rrt_band_rows.argtypes = [P(Band), ci]
     lib.rrt_assemble_bands.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
     lib.rrt_read_counters.argtypes = [vp, P(Counters), ci]

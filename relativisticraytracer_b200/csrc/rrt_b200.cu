@@ -1011,8 +1011,8 @@ struct rrt_context {
     unsigned int* d_tickets = nullptr;
     unsigned ticket_next = 0;
     int kernel_variant = 1;  // RRT_KERNEL_VARIANT: 1 tile-per-warp (default), 2 packed f32x2, 3 wavefront-in-warp (measured alternatives)
-    void* d_frame = nullptr;
-    size_t d_frame_bytes = 0;
+    void* d_frame[RRT_HOST_SLOTS] = {};  // device frames behind the host-destination calls, one per slot
+    size_t d_frame_bytes[RRT_HOST_SLOTS] = {};
     std::string err;
     std::mutex mu;
 };
@@ -1157,7 +1157,8 @@ void rrt_context_destroy(rrt_context* ctx) {
     cudaDeviceSynchronize();
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_tickets) cudaFree(ctx->d_tickets);
-    if (ctx->d_frame) cudaFree(ctx->d_frame);
+    for (void* f : ctx->d_frame)
+        if (f) cudaFree(f);
     delete ctx;
 }
 
@@ -1310,26 +1311,36 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     return RRT_OK;
 }
 
-int rrt_render_host(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
-                    uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba) {
+int rrt_render_host_async(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
+                          uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba, int slot, void* stream) {
     if (!ctx) return RRT_ERR_BAD_ARG;
-    if (!host_rgba || w <= 0 || h <= 0) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render_host: bad argument");
+    if (!host_rgba || w <= 0 || h <= 0 || slot < 0 || slot >= RRT_HOST_SLOTS)
+        return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render_host_async: bad argument");
     const size_t bytes = (size_t)w * h * 4;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         DevGuard g(ctx->device);
-        if (ctx->d_frame_bytes < bytes) {
-            if (ctx->d_frame) cudaFree(ctx->d_frame);
-            ctx->d_frame = nullptr;
-            ctx->d_frame_bytes = 0;
-            RRT_CU(ctx, cudaMalloc(&ctx->d_frame, bytes));
-            ctx->d_frame_bytes = bytes;
+        if (ctx->d_frame_bytes[slot] < bytes) {  // first use of this slot at this size (synchronous, like any cudaMalloc)
+            if (ctx->d_frame[slot]) cudaFree(ctx->d_frame[slot]);
+            ctx->d_frame[slot] = nullptr;
+            ctx->d_frame_bytes[slot] = 0;
+            RRT_CU(ctx, cudaMalloc(&ctx->d_frame[slot], bytes));
+            ctx->d_frame_bytes[slot] = bytes;
         }
     }
-    int rc = rrt_render(ctx, prm, cam, fx, sky_texture, time, w, h, nullptr, ctx->d_frame, RRT_OUT_FRAME, nullptr, nullptr);
+    int rc = rrt_render(ctx, prm, cam, fx, sky_texture, time, w, h, nullptr, ctx->d_frame[slot], RRT_OUT_FRAME, nullptr, stream);
     if (rc != RRT_OK) return rc;
     DevGuard g(ctx->device);
-    RRT_CU(ctx, cudaMemcpy(host_rgba, ctx->d_frame, bytes, cudaMemcpyDeviceToHost));
+    RRT_CU(ctx, cudaMemcpyAsync(host_rgba, ctx->d_frame[slot], bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return RRT_OK;
+}
+
+int rrt_render_host(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
+                    uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba) {
+    int rc = rrt_render_host_async(ctx, prm, cam, fx, sky_texture, time, w, h, host_rgba, 0, nullptr);
+    if (rc != RRT_OK) return rc;
+    DevGuard g(ctx->device);
+    RRT_CU(ctx, cudaStreamSynchronize(nullptr));
     return RRT_OK;
 }
 

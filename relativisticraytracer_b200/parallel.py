@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._capi import OUT_PACKED, Band
+from ._capi import HOST_SLOTS, OUT_PACKED, Band
 
 DEFAULT_GROUP = 8
 
@@ -102,3 +102,80 @@ class BandedFrame:
             return 2
         dist.gather(self.packed, None, dst=0)
         return 1
+
+
+class FramePipeline:
+    """A sequence of frames with ``depth`` of them in flight (the recorder loop of the reference renders frame
+    after frame, src/main.cpp:505-528).
+
+    Frame k runs on CUDA stream k % depth with its own buffers: trace of this rank's rows [+ NCCL gather to
+    rank 0 + rrt_assemble_bands there] [+ device->host copy into a pinned frame on rank 0].  Within one stream
+    the order is kept, between streams nothing waits, so the drain of frame k -- the few warps still
+    integrating the expensive disk-plane rays while most SMs are already idle -- overlaps with the start of
+    frame k+1 instead of leaving the GPU empty.  Every pixel is the same pure function of its frame's inputs
+    as in the unpipelined call, so results are identical.
+    """
+
+    def __init__(self, renderer, w: int, h: int, group: int = DEFAULT_GROUP, depth: int = 2, to_host: bool = False):
+        if not 1 <= depth <= HOST_SLOTS:
+            raise ValueError(f"depth must be 1..{HOST_SLOTS}")
+        self.r, self.w, self.h, self.group, self.depth, self.to_host = renderer, w, h, group, depth, to_host
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.band = Band(self.rank, self.world, group)
+        self.rows_max = max_band_rows(self.world, group, h)
+        dev = renderer.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        root = self.rank == 0
+        self.packed = [torch.zeros((self.rows_max, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if self.world > 1 else None
+        self.gathered = ([torch.zeros((self.world, self.rows_max, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)]
+                         if root and self.world > 1 else None)
+        need_dev_frame = root and (self.world > 1 or not to_host)
+        self.frames = [torch.zeros((h, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if need_dev_frame else None
+        self.host_frames = ([torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+                            if root and to_host else None)
+        self.submitted = 0
+
+    def begin(self) -> None:
+        """Order every pipeline stream after the work already queued on the current stream."""
+        cur = torch.cuda.current_stream(self.r.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def submit(self, prm, cam, fx, sky, time: float) -> int:
+        """Enqueue one frame; returns how many of OUR kernels that launched on this rank."""
+        k = self.submitted % self.depth
+        self.submitted += 1
+        s = self.streams[k]
+        if self.world == 1:
+            if self.to_host:   # the C-ABI call with a HOST destination, asynchronous flavour
+                self.r.render_host_async(prm, cam, fx, sky, time, self.w, self.h, self.host_frames[k], slot=k, stream=s)
+            else:
+                self.r.render(prm, cam, fx, sky, time, self.w, self.h, out=self.frames[k], stream=s)
+            return 1
+        launches = 1
+        with torch.cuda.stream(s):
+            self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.packed[k], layout=OUT_PACKED, stream=s)
+            if self.rank == 0:
+                dist.gather(self.packed[k], list(self.gathered[k].unbind(0)), dst=0)
+                self.r.assemble_bands(self.gathered[k], self.rows_max, self.w, self.h, self.world, self.group,
+                                      frame=self.frames[k], stream=s)
+                launches += 1
+                if self.to_host:
+                    self.host_frames[k].copy_(self.frames[k], non_blocking=True)
+            else:
+                dist.gather(self.packed[k], None, dst=0)
+        return launches
+
+    def end(self) -> None:
+        """Order the current stream after every frame submitted so far (no host synchronisation)."""
+        cur = torch.cuda.current_stream(self.r.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def last_frame(self):
+        """The most recently submitted frame's destination on rank 0 (host tensor if to_host, else device)."""
+        if self.rank != 0 or self.submitted == 0:
+            return None
+        k = (self.submitted - 1) % self.depth
+        return self.host_frames[k] if self.to_host else self.frames[k]

@@ -166,6 +166,18 @@ class Renderer:
         self._check(self._lib.rrt_render_host(self._ctx, C.byref(prm), C.byref(cam), C.byref(fx), C.c_uint64(tex),
                                               float(time), int(w), int(h), C.c_void_p(ptr)))
 
+    def render_host_async(self, prm: Params, cam: Camera, fx: Effects, sky: Sky | int, time: float, w: int, h: int,
+                          host_out: torch.Tensor, slot: int = 0, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """rrt_render_host_async: trace + device->host copy enqueued on `stream`, no synchronisation.
+        ``host_out`` must be a pinned CPU tensor; ``slot`` < HOST_SLOTS selects the context's device frame."""
+        tex = sky.texture if isinstance(sky, Sky) else int(sky)
+        assert (not host_out.is_cuda) and host_out.is_pinned() and host_out.is_contiguous()
+        assert host_out.numel() * host_out.element_size() >= w * h * 4
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._check(self._lib.rrt_render_host_async(self._ctx, C.byref(prm), C.byref(cam), C.byref(fx), C.c_uint64(tex),
+                                                    float(time), int(w), int(h), C.c_void_p(host_out.data_ptr()),
+                                                    int(slot), C.c_void_p(st.cuda_stream)))
+
     def assemble_bands(self, packed: torch.Tensor, rows_per_rank: int, w: int, h: int, nranks: int, group: int,
                        frame: Optional[torch.Tensor] = None, stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         if frame is None:
