@@ -147,48 +147,76 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
     // general path for its whole life.  Uniform per launch in practice (depends on the camera only).
     const bool fast_ok = rrt::dot3(p, p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
     const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
-#pragma unroll 1
-    for (; it < max_steps; ++it) {                                                        // :41
-        const float r2 = rrt::dot3(p, p);
-        const float r = rrt::sqrt_rn_fast(r2);                                            // :44
-        if (r < C.horizon_r) { captured = true; T = 0.0f; break; }                        // :47-51
-        bool disk_zone = false, dust_zone = false;
-        float h = C.h[0], h6 = C.h6[0];
-        if (r < zone_rmax) {  // 3/4 of all steps are outside every zone: one compare for them
-            const bool near_bh = r < 18.0f;                                               // :56
-            disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;                  // :57
-            dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;                  // :58
-            const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));           // :60-62
-            h = C.h[zi];
-            h6 = C.h6[zi];
+    // one compare per step for "redo with the general code": smallest stage radius below acc_rmin (or NaN), or
+    // the whole ray outside the fast domain (+inf: every step is redone)
+    const float redo_below = fast_ok ? C.acc_rmin : __int_as_float(0x7f800000);
+    // Two-level loop.  The inner loop holds what (nearly) every step needs -- the branch-free RK4 step and, in
+    // lock-step for the lanes that are inside a medium, the out-of-line media sample -- and nothing else; the
+    // general-domain redo of a step (practically never taken) is done by the outer loop, which then re-enters,
+    // so its call does not cost the hot loop registers or convergence barriers.  `it` counts executed
+    // integrate_rk4 calls on every path.
+    auto fold = [&](const MediaOut& m) {                                                      // :71, :107-115
+        if (m.dense) {
+            touched = true;
+            ++n_dense;
+            const float wgt = (1.0f - m.s) * T;                                               // :109
+            Ir += m.er * wgt; Ig += m.eg * wgt; Ib += m.eb * wgt;                             // :111-113
+            T *= m.s;                                                                         // :115
         }
-        const float hh = h * 0.5f;  // exact
-        const V3 q = p;  // pre-step position: media and the escape test use it (:68-69, :120)
-        const V3 v_in = v;
-        const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);           // :64
-        if (!fast_ok || rmin < C.acc_rmin) {
+    };
+    enum : int { kRanOut = 0, kCaptured = 1, kEscaped = 2, kRedo = 3 };
+    for (;;) {
+        int ev = kRanOut;
+        V3 q = p, v_in = v;   // pre-step state: media and the escape test use q (:68-69, :120)
+        float r = 0.0f, h = C.h[0], hh = C.hh[0], h6 = C.h6[0];
+        unsigned zones = 0;
+#pragma unroll 1
+        while (it < max_steps) {                                                              // :41
+            const float r2 = rrt::dot3(p, p);
+            r = rrt::sqrt_rn_fast(r2);                                                        // :44
+            if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
+            h = C.h[0]; h6 = C.h6[0];
+            unsigned z = 0;
+            if (r < zone_rmax) {  // 3/4 of all steps are outside every zone: one compare for them
+                const bool near_bh = r < 18.0f;                                               // :56
+                const bool disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;       // :57
+                const bool dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;       // :58
+                const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));           // :60-62
+                h = C.h[zi];
+                h6 = C.h6[zi];
+                if (MEDIA) z = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);   // :67
+            }
+            zones = z;
+            hh = h * 0.5f;  // exact
+            q = p;
+            v_in = v;
+            const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);           // :64
+            if (!(rmin >= redo_below)) { ev = kRedo; break; }
+            ++it;
+            if (MEDIA && z) {
+                n_disk += z & 1u;
+                n_dust += z >> 1;
+                fold(media_sample(C, q, v, r, h, A.time, z));
+            }
+            if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { ev = kEscaped; break; }               // :120
+        }
+        if (ev == kRedo) {
             // outside the branch-free domain, or geodesics.h:33 can fire: redo this step with the general code
             const PV s = rk4_step_general<SPIN>(C, q, v_in, h, hh, h6);
             p = s.p; v = s.v;
-        }
-        if (MEDIA && (disk_zone || dust_zone)) {                                          // :67
-            const unsigned zones = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);
-            n_disk += zones & 1u;
-            n_dust += zones >> 1;
-            if (zones) {
-                const MediaOut m = media_sample(C, q, v, r, h, A.time, zones);
-                if (m.dense) {                                                            // :71
-                    touched = true;
-                    ++n_dense;
-                    const float wgt = (1.0f - m.s) * T;                                   // :109
-                    Ir += m.er * wgt; Ig += m.eg * wgt; Ib += m.eb * wgt;                 // :111-113
-                    T *= m.s;                                                             // :115
-                }
+            ++it;
+            if (MEDIA && zones) {
+                n_disk += zones & 1u;
+                n_dust += zones >> 1;
+                fold(media_sample(C, q, v, r, h, A.time, zones));
             }
+            if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { escaped = true; break; }              // :120
+            continue;
         }
-        if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { escaped = true; ++it; break; }       // :120 (this step counted)
+        if (ev == kCaptured) { captured = true; T = 0.0f; }
+        escaped = ev == kEscaped;
+        break;
     }
-    // `it` counts executed integrate_rk4 calls on every exit path
     R.exhausted = !captured && !escaped;  // the for loop ran out (:41)
     R.steps = it;
     R.captured = captured;
