@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--flags", type=int, default=3, help="experiment only: media flags (3 = disk+dust = the headline workload)")
     ap.add_argument("--camera", default="C0", help="experiment only: C0 (headline) .. C3")
     ap.add_argument("--depth", type=int, default=2, help="frames in flight in the timed sequence (1 = one at a time)")
+    ap.add_argument("--workload", default="frame", choices=["frame", "path"],
+                    help="frame (default, the headline: one 4K frame cut into row bands) or path (BASELINE config 5: "
+                         "the 300-frame 'Gargantua Fly-By' at 1080p, frame k on GPU k mod N, sustained frames/s)")
+    ap.add_argument("--path-frames", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     return ap.parse_args()
@@ -156,6 +160,64 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+def run_path_workload(args, r, sky, prm, world, rank, dev):
+    """BASELINE config 5: 300 frames of the reference's 'Gargantua Fly-By' path (src/camera_paths.cpp:33-43) under
+    the recorder's 1/24 s clock at 1080p, frame k on GPU k mod N, frames gathered to rank 0 over NCCL and copied to
+    pinned host memory there (where the encoder would read them).  One timed pass over the whole path per step."""
+    import torch
+    import torch.distributed as dist
+    import relativisticraytracer_b200 as rrt
+    from relativisticraytracer_b200.parallel import PathSequence
+    w, h = (1920, 1080) if (args.width, args.height) == (W4K, H4K) else (args.width, args.height)
+    fx = rrt.default_effects()
+    seq = PathSequence(r, w, h, depth=max(1, min(args.depth, 4)))
+    n = args.path_frames
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    seq.render(0, min(n, 2 * world * seq.depth), prm, fx, sky)          # warm-up: a few rounds
+    barrier()
+    r.read_counters(reset=True)
+    times, launches = [], 0
+    with ClockSampler(dev) as clk:
+        for _ in range(max(1, args.steps)):
+            barrier()
+            t0 = time.perf_counter()
+            done, l = seq.render(0, n, prm, fx, sky)
+            barrier()
+            times.append(time.perf_counter() - t0)
+            launches += l
+    cnt = r.read_counters(reset=True)
+    tot = torch.tensor([cnt["rk4_steps"]], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    secs = float(tmax.item()) / len(times)
+    steps_per_pass = float(tot.item()) / len(times)
+    line = {
+        "metric": "geodesic_rk4_steps_per_s", "value": steps_per_pass / secs, "unit": "steps/s", "n_gpus": world,
+        "steps": len(times), "warmup": 1, "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{n}-frame Catmull-Rom camera path ('Gargantua Fly-By') at {w}x{h}, Kerr a=0.99 disk+dust, "
+                               f"frame-parallel across {world} GPU(s), frames gathered to rank 0 and copied to host",
+                   "frames": n, "fps_clock": 24, "frames_in_flight": seq.depth, "parallelism": f"frames{world}",
+                   "rk4_steps_per_pass": steps_per_pass},
+        "frames_per_s": n / secs,
+        "e2e": {"value": steps_per_pass / secs, "unit": "steps/s", "frames_per_s": n / secs,
+                "h2d_bytes_per_step": 164 * n, "d2h_bytes_per_step": w * h * 4 * n,
+                "timing": "host wall clock around the whole path incl. gathers, device->host copies and final synchronize"},
+        "gpu_launches": launches, "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
@@ -181,6 +243,11 @@ def main():
     r = rrt.Renderer(dev)
     sky = r.create_sky(rrt.procedural_sky(4096, 2048))
     prm = rrt.default_params(spin_a=SPIN, flags=args.flags)
+    if args.workload == "path":
+        run_path_workload(args, r, sky, prm, world, rank, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     cams = {"C0": (CAM_POS, CAM_YAW, CAM_PITCH), "C1": ((15.0, 3.0, -30.0), -26.6, -5.1),
             "C2": ((35.0, 0.8, 10.0), -106.0, -1.2), "C3": ((4.2, 0.6, 4.2), -90.0, -5.7)}
     cam = rrt.camera_state_from(*cams[args.camera])

@@ -30,6 +30,7 @@ extern "C" {
 #define RRT_ERR_CUDA (-2)      /* a CUDA runtime call or the kernel failed; see rrt_last_error() */
 #define RRT_ERR_NO_DEVICE (-3) /* no usable sm_100 device */
 #define RRT_ERR_NOMEM (-4)
+#define RRT_ERR_IO (-5)        /* frame sink: open / write / close failed */
 
 /* ---- parameter surface ---------------------------------------------------------------------------
  * The reference bakes these in as macros (include/config.h); here they are run-time fields with the
@@ -197,6 +198,26 @@ int rrt_path_num_keys(int path_index);
 float rrt_path_duration(int path_index);
 int rrt_path_state(int path_index, float t, rrt_camera* out, float pos_yaw_pitch[5]);
 float rrt_path_clock(int frame, float fps);
+
+/* ---- frame sink: the step after the hot path ----------------------------------------------------------
+ * Pure host code.  Replaces, for headless use, the reference's ScreenRecorder (src/main.cpp:29-124): frames
+ * are the host copies of what launch_raymarch / rrt_render_host wrote (w*h*4 bytes, buffer row 0 first --
+ * which is what the recorder's glReadPixels returns for the 1:1 quad it draws).
+ *   RRT_SINK_RGBA  the recorder's wire format byte for byte: raw rgba frames back to back (src/main.cpp:85-97).
+ *                  With target "|<command>" the stream is popen()ed exactly like the reference does; the
+ *                  reference's own command line is produced by rrt_sink_ffmpeg_command (src/main.cpp:61-72).
+ *   RRT_SINK_Y4M   YUV4MPEG2 4:2:0 (BT.601 studio range), rows already flipped as `-vf vflip` would: a
+ *                  self-describing file for boxes without ffmpeg.
+ * target: a file path, or "|command". */
+#define RRT_SINK_RGBA 0
+#define RRT_SINK_Y4M 1
+typedef struct rrt_sink rrt_sink;
+int rrt_sink_open(const char* target, int format, int w, int h, int fps, rrt_sink** out);
+int rrt_sink_write(rrt_sink* sink, const uint8_t* host_rgba);
+int rrt_sink_frames(const rrt_sink* sink);          /* frames written so far */
+int rrt_sink_close(rrt_sink* sink);                 /* RRT_ERR_IO if the file / pipe reported an error */
+/* writes the reference recorder's ffmpeg command for this size into buf; returns its length or RRT_ERR_BAD_ARG */
+int rrt_sink_ffmpeg_command(int w, int h, int fps, const char* out_name, char* buf, int buflen);
 
 /* ---- measurement helper ---------------------------------------------------------------------------
  * Register-resident FFMA-chain microbenchmark: the FP32 roofline denominator MEASURED_PEAKS.json lacks.

@@ -10,6 +10,8 @@ from ._capi import (Band, Camera, Counters, Effects, Params, Planes, RrtError, F
                     default_effects, default_params, effects_off)
 from .renderer import (CameraEffects, CameraState, Renderer, Sky, camera_state_from, launch_raymarch, path_clock,
                        path_duration, path_names, path_state, set_launch_params)
-from .skybox import procedural_sky
+from .skybox import load_skybox, procedural_sky
+from .sink import FrameSink, ffmpeg_command
+from ._capi import SINK_RGBA, SINK_Y4M, HOST_SLOTS
 
 __all__ = [n for n in dir() if not n.startswith("_")]

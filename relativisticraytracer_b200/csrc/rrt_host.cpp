@@ -7,7 +7,11 @@
 // tables of src/camera_paths.cpp.  Built with -ffp-contract=off: every operation is one binary32 op in
 // the reference's order, so the basis vectors are bit-identical to the reference's on the same libm.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <new>
+#include <string>
+#include <vector>
 
 #include "../../include/rrt.h"
 
@@ -126,6 +130,108 @@ float rrt_path_clock(int frame, float fps) {
     const float dt = 1.0f / fps;
     for (int i = 0; i < frame; ++i) t = t + dt;
     return t;
+}
+
+// ---- frame sink: the step immediately after the hot path --------------------------------------------------
+// The reference's ScreenRecorder (src/main.cpp:29-124) reads the window back with glReadPixels -- which, for the
+// 1:1 textured quad it draws (src/main.cpp:404-409, 471-479), returns exactly the bytes launch_raymarch wrote,
+// buffer row 0 first -- and fwrite()s each frame to `ffmpeg -f rawvideo -pix_fmt rgba -s WxH -r 24 -i - -vf vflip
+// ...` (src/main.cpp:61-72, 85-97).  RRT_SINK_RGBA writes that wire format byte for byte; a target that starts
+// with '|' is popen()ed like the reference does, so "|ffmpeg ..." reproduces the recorder on a box that has
+// ffmpeg.  RRT_SINK_Y4M writes a self-describing YUV4MPEG2 4:2:0 file with the rows already flipped (what
+// -vf vflip -pix_fmt yuv420p would hand to the encoder), BT.601 studio range, for boxes without ffmpeg.
+}  // extern "C"
+
+struct rrt_sink {
+    FILE* f = nullptr;
+    bool piped = false;
+    int format = 0, w = 0, h = 0, frames = 0;
+    std::vector<uint8_t> yuv;
+};
+
+extern "C" {
+
+int rrt_sink_ffmpeg_command(int w, int h, int fps, const char* out_name, char* buf, int buflen) {
+    if (!buf || buflen <= 0 || !out_name || w <= 0 || h <= 0 || fps <= 0) return RRT_ERR_BAD_ARG;
+    // src/main.cpp:61-72, same options in the same order
+    const int n = std::snprintf(buf, (size_t)buflen,
+                                "ffmpeg -y -f rawvideo -pix_fmt rgba -s %dx%d -r %d -i - -vf vflip -c:v libx264 -preset fast "
+                                "-crf 18 -pix_fmt yuv420p \"%s\"",
+                                w, h, fps, out_name);
+    return (n < 0 || n >= buflen) ? RRT_ERR_BAD_ARG : n;
+}
+
+int rrt_sink_open(const char* target, int format, int w, int h, int fps, rrt_sink** out) {
+    if (!out) return RRT_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!target || !*target || w <= 0 || h <= 0 || fps <= 0 || (format != RRT_SINK_RGBA && format != RRT_SINK_Y4M))
+        return RRT_ERR_BAD_ARG;
+    rrt_sink* s = new (std::nothrow) rrt_sink();
+    if (!s) return RRT_ERR_NOMEM;
+    s->format = format; s->w = w; s->h = h;
+    s->piped = target[0] == '|';
+    s->f = s->piped ? popen(target + 1, "w") : std::fopen(target, "wb");
+    if (!s->f) { delete s; return RRT_ERR_IO; }   // like the recorder's "Failed to start FFmpeg" (src/main.cpp:75-78)
+    if (format == RRT_SINK_Y4M) {
+        s->yuv.resize((size_t)w * h + 2 * (size_t)((w + 1) / 2) * ((h + 1) / 2));
+        if (std::fprintf(s->f, "YUV4MPEG2 W%d H%d F%d:1 Ip A1:1 C420jpeg\n", w, h, fps) < 0) {
+            rrt_sink_close(s);
+            return RRT_ERR_IO;
+        }
+    }
+    *out = s;
+    return RRT_OK;
+}
+
+int rrt_sink_write(rrt_sink* s, const uint8_t* host_rgba) {
+    if (!s || !s->f || !host_rgba) return RRT_ERR_BAD_ARG;
+    const int w = s->w, h = s->h;
+    if (s->format == RRT_SINK_RGBA) {
+        const size_t n = (size_t)w * h * 4;
+        if (std::fwrite(host_rgba, 1, n, s->f) != n) return RRT_ERR_IO;   // "Frame write incomplete", src/main.cpp:93-95
+    } else {
+        // vflip: output row j is buffer row h-1-j
+        const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+        uint8_t* Y = s->yuv.data();
+        uint8_t* U = Y + (size_t)w * h;
+        uint8_t* V = U + (size_t)cw * ch;
+        auto px = [&](int x, int j) { return host_rgba + ((size_t)(h - 1 - j) * w + x) * 4; };
+        for (int j = 0; j < h; ++j)
+            for (int x = 0; x < w; ++x) {
+                const uint8_t* p = px(x, j);
+                Y[(size_t)j * w + x] = (uint8_t)(((66 * p[0] + 129 * p[1] + 25 * p[2] + 128) >> 8) + 16);
+            }
+        for (int cj = 0; cj < ch; ++cj)
+            for (int cx = 0; cx < cw; ++cx) {
+                int r = 0, g = 0, b = 0;
+                for (int dy = 0; dy < 2; ++dy)
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const int x = 2 * cx + dx < w ? 2 * cx + dx : w - 1, j = 2 * cj + dy < h ? 2 * cj + dy : h - 1;
+                        const uint8_t* p = px(x, j);
+                        r += p[0]; g += p[1]; b += p[2];
+                    }
+                r = (r + 2) >> 2; g = (g + 2) >> 2; b = (b + 2) >> 2;
+                U[(size_t)cj * cw + cx] = (uint8_t)(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128);
+                V[(size_t)cj * cw + cx] = (uint8_t)(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128);
+            }
+        if (std::fputs("FRAME\n", s->f) < 0 || std::fwrite(s->yuv.data(), 1, s->yuv.size(), s->f) != s->yuv.size())
+            return RRT_ERR_IO;
+    }
+    ++s->frames;
+    return RRT_OK;
+}
+
+int rrt_sink_frames(const rrt_sink* s) { return s ? s->frames : RRT_ERR_BAD_ARG; }
+
+int rrt_sink_close(rrt_sink* s) {
+    if (!s) return RRT_ERR_BAD_ARG;
+    int rc = RRT_OK;
+    if (s->f) {
+        const int e = s->piped ? pclose(s->f) : std::fclose(s->f);
+        if (e != 0) rc = RRT_ERR_IO;
+    }
+    delete s;
+    return rc;
 }
 
 }  // extern "C"

@@ -179,3 +179,84 @@ class FramePipeline:
             return None
         k = (self.submitted - 1) % self.depth
         return self.host_frames[k] if self.to_host else self.frames[k]
+
+
+class PathSequence:
+    """Frame-parallel rendering of a keyframe camera path (BASELINE config 5; reference P + R keys:
+    PathController playback under the recorder's fixed 1/fps clock, src/main.cpp:171-220, 505-528).
+
+    Frames are 1-based like the recorder counts them.  Round j covers frames j*N+1 .. j*N+N; rank r renders
+    frame j*N+r+1 whole (``frame_owner``), one NCCL gather per round brings the N frames to rank 0 (the
+    encoding GPU), which copies them to pinned host memory and hands them to the sink in frame order.  Rounds
+    are pipelined ``depth`` deep on separate streams like ``FramePipeline``.  Camera and clock come from the
+    C-ABI host functions (``rrt_path_state`` / ``rrt_path_clock``), so frame k is the same pure function of k
+    on every rank count."""
+
+    def __init__(self, renderer, w: int, h: int, depth: int = 2):
+        if not 1 <= depth <= HOST_SLOTS:
+            raise ValueError(f"depth must be 1..{HOST_SLOTS}")
+        self.r, self.w, self.h, self.depth = renderer, w, h, depth
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        dev = renderer.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        root = self.rank == 0
+        self.local = [torch.zeros((h, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if self.world > 1 else None
+        self.gathered = ([torch.zeros((self.world, h, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)]
+                         if root and self.world > 1 else None)
+        self.host = [torch.zeros((self.world, h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(depth)] if root else None
+
+    def render(self, path_index: int, n_frames: int, prm, fx, sky, fps: float = 24.0, sink=None, first_frame: int = 1):
+        """Render frames first_frame .. first_frame+n_frames-1 of the path.  Returns (frames_done, launches)."""
+        from .renderer import path_clock, path_state
+        cur = torch.cuda.current_stream(self.r.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+        rounds = (n_frames + self.world - 1) // self.world
+        in_flight = [None] * self.depth     # per slot: list of frame numbers it holds
+        launches = done = 0
+
+        def retire(k):
+            nonlocal done
+            if in_flight[k] is None:
+                return
+            self.events[k].synchronize()
+            if self.rank == 0:
+                for i, f in enumerate(in_flight[k]):
+                    if f is not None:
+                        if sink is not None:
+                            sink.write(self.host[k][i])
+                        done += 1
+            in_flight[k] = None
+
+        for j in range(rounds):
+            k = j % self.depth
+            retire(k)
+            frames = [first_frame + j * self.world + r if j * self.world + r < n_frames else None for r in range(self.world)]
+            mine = frames[self.rank]
+            s = self.streams[k]
+            with torch.cuda.stream(s):
+                if self.world == 1:
+                    t = path_clock(mine, fps)
+                    cam, _ = path_state(path_index, t)
+                    self.r.render_host_async(prm, cam, fx, sky, t, self.w, self.h, self.host[k][0], slot=k, stream=s)
+                    launches += 1
+                else:
+                    if mine is not None:
+                        t = path_clock(mine, fps)
+                        cam, _ = path_state(path_index, t)
+                        self.r.render(prm, cam, fx, sky, t, self.w, self.h, out=self.local[k], stream=s)
+                        launches += 1
+                    if self.rank == 0:
+                        dist.gather(self.local[k], list(self.gathered[k].unbind(0)), dst=0)
+                        self.host[k].copy_(self.gathered[k], non_blocking=True)
+                    else:
+                        dist.gather(self.local[k], None, dst=0)
+                self.events[k].record(s)
+            in_flight[k] = frames
+        for j in range(rounds, rounds + self.depth):
+            retire(j % self.depth)
+        for s in self.streams:
+            cur.wait_stream(s)
+        return done, launches

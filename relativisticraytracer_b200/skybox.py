@@ -36,3 +36,51 @@ def procedural_sky(width: int = 4096, height: int = 2048, seed: int = 1234, star
     out[..., :3] = np.clip(np.floor(img * 255.0 + 0.5), 0, 255).astype(np.uint8)
     out[..., 3] = 255
     return out
+
+
+def load_skybox(path: str, width: int | None = None, height: int | None = None) -> np.ndarray:
+    """Host half of the reference's ``loadSkybox`` (src/main.cpp:237-245): decode an equirectangular image file
+    into the RGBA8, rows-top-down array ``stbi_load(path, &w, &h, &c, 4)`` returns, ready for
+    ``Renderer.create_sky`` (the device half, src/main.cpp:246-263).
+
+    * ``.png`` / ``.jpg`` / anything PIL opens: decoded with PIL.  PNG decoding is lossless, so the bytes equal
+      stb_image's.  JPEG decoders are allowed to differ in their IDCT / chroma upsampling: PIL (libjpeg) and
+      stb_image v2.30 give slightly different bytes for ``skybox2.jpg``; for byte-level
+      parity with a reference build on a JPEG asset, decode once with the reference's decoder and ship ``.npy``.
+    * ``.npy``: an array saved with ``numpy.save`` ([h, w, 3] or [h, w, 4] uint8).
+    * ``.rgba`` / ``.raw``: headerless RGBA8, ``width`` and ``height`` required.
+
+    Grey and grey+alpha sources are expanded the way stb_image does for ``req_comp = 4`` (grey replicated to
+    RGB, missing alpha = 255)."""
+    ext = path.rsplit(".", 1)[-1].lower() if "." in path else ""
+    if ext == "npy":
+        img = np.load(path)
+    elif ext in ("rgba", "raw"):
+        if not width or not height:
+            raise ValueError("raw RGBA skybox needs width and height")
+        img = np.fromfile(path, dtype=np.uint8)
+        if img.size != width * height * 4:
+            raise ValueError(f"{path}: expected {width * height * 4} bytes, found {img.size}")
+        img = img.reshape(height, width, 4)
+    else:
+        from PIL import Image
+        with Image.open(path) as im:
+            if im.mode not in ("RGB", "RGBA", "L", "LA"):
+                im = im.convert("RGBA")
+            img = np.asarray(im)
+    img = np.asarray(img)
+    if img.dtype != np.uint8:
+        raise ValueError("skybox must be 8 bits per channel")
+    if img.ndim == 2:
+        img = img[..., None]
+    if img.ndim != 3 or img.shape[2] not in (1, 2, 3, 4):
+        raise ValueError(f"unsupported skybox shape {img.shape}")
+    h, w, c = img.shape
+    out = np.empty((h, w, 4), np.uint8)
+    if c >= 3:
+        out[..., :3] = img[..., :3]
+        out[..., 3] = img[..., 3] if c == 4 else 255
+    else:
+        out[..., :3] = img[..., :1]
+        out[..., 3] = img[..., 1] if c == 2 else 255
+    return out
