@@ -56,6 +56,13 @@ typedef struct rrt_params {
 
 #define RRT_FLAG_DISK 1u /* accretion-disk medium  (getAccretionDensity, raymarcher.cu:68) */
 #define RRT_FLAG_DUST 2u /* dust-cloud medium      (getDustCloudDensity, raymarcher.cu:69) */
+/* Rounding contract.  Default (flag clear): every a*b+c is a rounded multiply followed by a rounded add --
+ * the reference's expressions without contraction, bit-identical to its headers compiled for a host with
+ * -ffp-contract=off.  RRT_FLAG_FMAD: the arithmetic of the reference's OWN CUDA build -- nvcc's default
+ * -fmad=true fuses a*b+c into FMA, and the geodesic / ray-setup / noise code follows, operation by operation,
+ * the fusion schedule nvcc 12.9 emits for the reference's sources on sm_100a (see DESIGN.md "Rounding
+ * contracts"); ~1.3x fewer FP32 instructions per RK4 step. */
+#define RRT_FLAG_FMAD 4u
 
 /* struct CameraState, include/raymarcher.h:11-16: four packed float3, 48 bytes. */
 typedef struct rrt_camera {
@@ -230,6 +237,10 @@ int rrt_fp32_peak_probe(rrt_context* ctx, int iters, double* tflops, double* ms)
  * of results that differ in value (expected: 0 and 0). */
 int rrt_exact_math_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_t* div_mismatches,
                             uint64_t* sqrt_mismatches);
+
+/* Rounding contract of the probes that take no rrt_params (hash31 / noise3D / fbm): 0 strict (default), 1 the
+ * RRT_FLAG_FMAD contract.  The other probes and rrt_render follow rrt_params.flags. */
+int rrt_set_probe_contract(rrt_context* ctx, int fmad);
 
 #ifdef __cplusplus
 }

@@ -149,6 +149,13 @@ class Oracle:
         self._fn("disk_density").argtypes = [P(Params), C.c_int, vp, C.c_float, vp]
         self._fn("dust_density").argtypes = [P(Params), C.c_int, vp, C.c_float, vp]
         self._fn("tex2d").argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+        if self.kind == "port":
+            self.lib.ora_set_probe_contract.argtypes = [C.c_int]
+
+    def set_probe_contract(self, fmad: bool) -> None:
+        """Contract of hash31 / noise3d / fbm (the probes without a parameter block); port only."""
+        assert self.kind == "port"
+        self.lib.ora_set_probe_contract(1 if fmad else 0)
 
     # ---- parameter helpers -------------------------------------------------------------
     def default_params(self, **over) -> Params:

@@ -54,6 +54,11 @@ typedef struct ora_params {
 
 #define ORA_FLAG_DISK 1u  /* evaluate getAccretionDensity in the disk zone  (raymarcher.cu:68) */
 #define ORA_FLAG_DUST 2u  /* evaluate getDustCloudDensity in the cloud zone (raymarcher.cu:69) */
+/* PORT ONLY (rrt_oracle.c): evaluate with the FMA fusion schedule of the reference's own CUDA build (nvcc default
+ * -fmad=true, read off the SASS of raymarch_kernel) instead of the unfused host arithmetic -- the CPU twin of
+ * the product's RRT_FLAG_FMAD contract.  The reference-header build (ref_harness.cpp) ignores the flag: g++
+ * compiles those headers with -ffp-contract=off. */
+#define ORA_FLAG_FMAD 4u
 
 /* struct CameraState, include/raymarcher.h:11-16 (four packed float3). */
 typedef struct ora_camera {

@@ -33,36 +33,53 @@ typedef struct { float x, y, z; } v3;
 
 static const float K_PI = 3.1415926535f; /* math_utils.h:7 */
 
+/* ---- rounding contracts ------------------------------------------------------------------------
+ * fm = 0 (default): the reference's expressions exactly as written, no contraction (this file is built with
+ *   -ffp-contract=off) -- the twin of the reference headers compiled for the host.
+ * fm = 1 (ORA_FLAG_FMAD): the twin of the reference's own CUDA build.  nvcc's default -fmad=true fuses a*b+c;
+ *   which operations it fuses for the reference's sources (nvcc 12.9, sm_100a) was read off the SASS of
+ *   raymarch_kernel and is restated here operation by operation with fmaf(): add(x, y) with x a product ->
+ *   fma(x.a, x.b, y), else with y a product -> fma(y.a, y.b, x), plus the two places where the kernel deviates
+ *   from that rule (loop-header |p|^2, first RK4 stage's radial + drag sum).  Covers ray setup, the geodesic
+ *   integration, the value noise and the final assembly; the density / redshift expressions stay unfused here
+ *   (on the device they are left to nvcc), which moves them by ulps only. */
+static inline float mad(int fm, float a, float b, float c) { return fm ? fmaf(a, b, c) : a * b + c; }           /* a*b + c */
+static inline float msub2(int fm, float a, float b, float c, float d) { return fm ? fmaf(a, b, -(c * d)) : a * b - c * d; }
+static inline float mad2(int fm, float a, float b, float c, float d) { return fm ? fmaf(a, b, c * d) : a * b + c * d; }
+
 /* ---- float3 helpers, math_utils.h:11-48 ------------------------------------------------------ */
 static inline v3 V(float x, float y, float z) { v3 r = {x, y, z}; return r; }
-static inline float v_dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }                 /* :11-13 */
-static inline v3 v_cross(v3 a, v3 b) {                                                              /* :15-17 */
-    return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+static inline float v_dot(int fm, v3 a, v3 b) {                                                     /* :11-13 */
+    return fm ? fmaf(a.z, b.z, fmaf(a.x, b.x, a.y * b.y)) : a.x * b.x + a.y * b.y + a.z * b.z;
 }
-static inline float v_len(v3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }                /* :19-21 */
-static inline v3 v_unit(v3 a) {                                                                     /* :23-27 */
-    float m = v_len(a);
+static inline v3 v_cross(int fm, v3 a, v3 b) {                                                      /* :15-17 */
+    return V(msub2(fm, a.y, b.z, a.z, b.y), msub2(fm, a.z, b.x, a.x, b.z), msub2(fm, a.x, b.y, a.y, b.x));
+}
+static inline float v_len(int fm, v3 a) { return sqrtf(v_dot(fm, a, a)); }                          /* :19-21 */
+static inline v3 v_unit(int fm, v3 a) {                                                             /* :23-27 */
+    float m = v_len(fm, a);
     if (m < 1e-6f) return V(0, 0, 0);
     return V(a.x / m, a.y / m, a.z / m);
 }
 static inline v3 v_sub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }                   /* :29-31 */
 static inline v3 v_add(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }                   /* :33-35 */
 static inline v3 v_scale(v3 a, float s) { return V(a.x * s, a.y * s, a.z * s); }                    /* :37-39 */
-static inline float mixf(float a, float b, float t) { return a + t * (b - a); }                     /* :41-43 */
+static inline v3 v_axpy(int fm, v3 y, v3 x, float a) { return V(mad(fm, x.x, a, y.x), mad(fm, x.y, a, y.y), mad(fm, x.z, a, y.z)); } /* y + x*a */
+static inline float mixf(int fm, float a, float b, float t) { return mad(fm, t, b - a, a); }        /* :41-43 */
 static inline float sstep(float e0, float e1, float x) {                                            /* :45-48 */
     float t = fminf(fmaxf((x - e0) / (e1 - e0), 0.0f), 1.0f);
     return t * t * (3.0f - 2.0f * t);
 }
 
 /* ---- value noise, math_utils.h:91-121 -------------------------------------------------------- */
-static float hash31(v3 p) {                                                                         /* :91-96 */
+static float hash31(int fm, v3 p) {                                                                 /* :91-96 */
     float a = fmodf(p.x * 0.1031f, 1.0f), b = fmodf(p.y * 0.1031f, 1.0f), c = fmodf(p.z * 0.1031f, 1.0f);
-    float d = a * (b + 33.33f) + b * (c + 33.33f) + c * (a + 33.33f);
+    float d = v_dot(fm, V(a, b, c), V(b + 33.33f, c + 33.33f, a + 33.33f));
     a += d; b += d; c += d;
     return fmodf((a + b) * c, 1.0f);
 }
 
-static float noise3(v3 p) {                                                                         /* :98-110 */
+static float noise3(int fm, v3 p) {                                                                 /* :98-110 */
     v3 i = V(floorf(p.x), floorf(p.y), floorf(p.z));
     v3 f = V(p.x - i.x, p.y - i.y, p.z - i.z);
     float ux = f.x * f.x * (3.0f - 2.0f * f.x);
@@ -71,43 +88,54 @@ static float noise3(v3 p) {                                                     
     float c[2][2][2];
     for (int dz = 0; dz < 2; ++dz)
         for (int dy = 0; dy < 2; ++dy)
-            for (int dx = 0; dx < 2; ++dx) c[dz][dy][dx] = hash31(v_add(i, V((float)dx, (float)dy, (float)dz)));
-    float lo = mixf(mixf(c[0][0][0], c[0][0][1], ux), mixf(c[0][1][0], c[0][1][1], ux), uy);
-    float hi = mixf(mixf(c[1][0][0], c[1][0][1], ux), mixf(c[1][1][0], c[1][1][1], ux), uy);
-    return mixf(lo, hi, uz);
+            for (int dx = 0; dx < 2; ++dx) c[dz][dy][dx] = hash31(fm, v_add(i, V((float)dx, (float)dy, (float)dz)));
+    float lo = mixf(fm, mixf(fm, c[0][0][0], c[0][0][1], ux), mixf(fm, c[0][1][0], c[0][1][1], ux), uy);
+    float hi = mixf(fm, mixf(fm, c[1][0][0], c[1][0][1], ux), mixf(fm, c[1][1][0], c[1][1][1], ux), uy);
+    return mixf(fm, lo, hi, uz);
 }
 
-static float fbm(v3 p, int octaves) {                                                               /* :112-121 */
+static float fbm(int fm, v3 p, int octaves) {                                                       /* :112-121 */
     float acc = 0.0f, amp = 0.5f;
     for (int k = 0; k < octaves; ++k) {
-        acc += amp * noise3(p);
-        p = V(p.x * 2.05f + 10.0f, p.y * 2.05f + 10.0f, p.z * 2.05f + 10.0f);
+        acc = mad(fm, amp, noise3(fm, p), acc);
+        p = V(mad(fm, p.x, 2.05f, 10.0f), mad(fm, p.y, 2.05f, 10.0f), mad(fm, p.z, 2.05f, 10.0f));
         amp *= 0.5f;
     }
     return acc;
 }
 
 /* ---- geodesics.h ----------------------------------------------------------------------------- */
-static v3 geodesic_acc(const ora_params* P, v3 q, v3 v) {                                           /* geodesics.h:30-45 */
-    float r2 = v_dot(q, q);
+#define FM(P) (((P)->flags & ORA_FLAG_FMAD) != 0)
+/* r2 is |q|^2 as the caller's contract computes it; `first` marks the first RK4 stage (see "rounding contracts") */
+static v3 geodesic_acc_r2(const ora_params* P, v3 q, v3 v, float r2, int first) {                   /* geodesics.h:30-45 */
+    const int fm = FM(P);
     float r = sqrtf(r2);
     if (r < P->event_horizon * 0.5f) return V(0, 0, 0);
-    v3 L = v_cross(q, v);
-    float L2 = v_dot(L, L);
+    v3 L = v_cross(fm, q, v);
+    float L2 = v_dot(fm, L, L);
     float radial = -1.5f * P->event_horizon * L2 / (r2 * r2 * r);
-    v3 a_rad = v_scale(q, radial);
-    v3 axis_x_q = v_cross(V(0, 1, 0), q);                  /* SPIN_AXIS, config.h:22 */
     float drag = (2.0f * P->spin_a * P->event_horizon) / (r2 * r);
-    return v_add(a_rad, v_scale(axis_x_q, drag));
+    if (!fm) {
+        v3 a_rad = v_scale(q, radial);
+        v3 axis_x_q = v_cross(0, V(0, 1, 0), q);           /* SPIN_AXIS, config.h:22 */
+        return v_add(a_rad, v_scale(axis_x_q, drag));
+    }
+    /* cross((0,1,0), q) = (q.z, +-0, -q.x) exactly for finite q */
+    if (first) return V(fmaf(q.x, radial, q.z * drag), q.y * radial, fmaf(q.z, radial, -q.x * drag));
+    return V(fmaf(q.z, drag, q.x * radial), q.y * radial, fmaf(-q.x, drag, q.z * radial));
 }
+static v3 geodesic_acc(const ora_params* P, v3 q, v3 v) { return geodesic_acc_r2(P, q, v, v_dot(FM(P), q, q), 0); }
+/* |p|^2 of the loop header (raymarcher.cu:43-44), shared with the first RK4 stage */
+static inline float norm2_loop(int fm, v3 p) { return fm ? fmaf(p.y, p.y, p.x * p.x) + p.z * p.z : v_dot(0, p, p); }
 
 static float redshift_factor(const ora_params* P, v3 q, v3 ray_v) {                                 /* geodesics.h:11-25 */
-    float r = v_len(q);
+    const int fm = FM(P);
+    float r = v_len(fm, q);
     if (r < P->event_horizon * 1.01f) return 0.0f;
     float g_grav = sqrtf(1.0f - P->event_horizon / r);
     float beta = 1.0f / (powf(r, 1.5f) + P->spin_a);
-    v3 gas = v_unit(V(-q.z, 0, q.x));
-    float mu = v_dot(ray_v, gas);
+    v3 gas = v_unit(fm, V(-q.z, 0, q.x));
+    float mu = v_dot(fm, ray_v, gas);
     float gamma = 1.0f / sqrtf(1.0f - beta * beta);
     float g_dop = 1.0f / (gamma * (1.0f - beta * mu));
     return g_grav * g_dop;
@@ -115,26 +143,30 @@ static float redshift_factor(const ora_params* P, v3 q, v3 ray_v) {             
 
 /* ---- integrators.h ---------------------------------------------------------------------------- */
 static void step_euler(const ora_params* P, v3* p, v3* v, float h) {                                /* integrators.h:12-18 */
+    const int fm = FM(P);
     v3 q = v_sub(*p, V(0, 0, 0));
     v3 a = geodesic_acc(P, q, *v);
-    *p = v_add(*p, v_scale(*v, h));
-    *v = v_add(*v, v_scale(a, h));
+    *p = v_axpy(fm, *p, *v, h);
+    *v = v_axpy(fm, *v, a, h);
 }
 
 static void step_rk4(const ora_params* P, v3* p, v3* v, float h) {                                  /* integrators.h:23-59 */
+    const int fm = FM(P);
     const v3 origin = V(0.0f, 0.0f, 0.0f);                 /* MASS_POS, config.h:30 */
     v3 p0 = *p, v0 = *v;
-    v3 kv1 = geodesic_acc(P, v_sub(p0, origin), v0), kp1 = v0;
-    v3 v2 = v_add(v0, v_scale(kv1, h * 0.5f));
-    v3 kv2 = geodesic_acc(P, v_sub(v_add(p0, v_scale(kp1, h * 0.5f)), origin), v2), kp2 = v2;
-    v3 v3_ = v_add(v0, v_scale(kv2, h * 0.5f));
-    v3 kv3 = geodesic_acc(P, v_sub(v_add(p0, v_scale(kp2, h * 0.5f)), origin), v3_), kp3 = v3_;
-    v3 v4 = v_add(v0, v_scale(kv3, h));
-    v3 kv4 = geodesic_acc(P, v_sub(v_add(p0, v_scale(kp3, h)), origin), v4), kp4 = v4;
+    v3 q1 = v_sub(p0, origin);
+    v3 kv1 = geodesic_acc_r2(P, q1, v0, norm2_loop(fm, q1), 1), kp1 = v0;
+    v3 v2 = v_axpy(fm, v0, kv1, h * 0.5f);
+    v3 kv2 = geodesic_acc(P, v_sub(v_axpy(fm, p0, kp1, h * 0.5f), origin), v2), kp2 = v2;
+    v3 v3_ = v_axpy(fm, v0, kv2, h * 0.5f);
+    v3 kv3 = geodesic_acc(P, v_sub(v_axpy(fm, p0, kp2, h * 0.5f), origin), v3_), kp3 = v3_;
+    v3 v4 = v_axpy(fm, v0, kv3, h);
+    v3 kv4 = geodesic_acc(P, v_sub(v_axpy(fm, p0, kp3, h), origin), v4), kp4 = v4;
+    /* 2*x is exact, so k + 2*k' rounds the same fused or not */
     v3 kv = v_add(kv1, v_add(v_scale(kv2, 2.0f), v_add(v_scale(kv3, 2.0f), kv4)));
     v3 kp = v_add(kp1, v_add(v_scale(kp2, 2.0f), v_add(v_scale(kp3, 2.0f), kp4)));
-    *v = v_add(*v, v_scale(kv, h / 6.0f));
-    *p = v_add(*p, v_scale(kp, h / 6.0f));
+    *v = v_axpy(fm, *v, kv, h / 6.0f);
+    *p = v_axpy(fm, *p, kp, h / 6.0f);
 }
 
 /* ---- densities.h ------------------------------------------------------------------------------ */
@@ -144,7 +176,8 @@ static float disk_temperature(const ora_params* P, float r) {                   
 }
 
 static float disk_density(const ora_params* P, v3 p, float time) {                                  /* densities.h:20-62 */
-    float r = v_len(V(p.x, 0.0f, p.z));
+    const int fm = FM(P);
+    float r = v_len(0, V(p.x, 0.0f, p.z));   /* (x*x + 0*0) + z*z, unfused in both contracts */
     if (r < P->isco_radius || r > P->disk_out) return 0.0f;
     float taper = 1.0f;
     float taper_from = P->disk_out * 0.85f;
@@ -162,7 +195,7 @@ static float disk_density(const ora_params* P, v3 p, float time) {              
     v3 rot = V(r * cosf(ang), p.y * 4.0f, r * sinf(ang));
     float evo = time * 0.35f;
     v3 nc = v_add(v_scale(rot, 0.45f), V(0, evo, 0));
-    float n = fbm(nc, 5);
+    float n = fbm(fm, nc, 5);
     float streak = fmaxf(0.0f, n - 0.32f);
     streak = powf(streak * 2.8f, 1.6f);
     streak = fminf(6.0f, streak);
@@ -170,7 +203,8 @@ static float disk_density(const ora_params* P, v3 p, float time) {              
 }
 
 static float dust_density(const ora_params* P, v3 p, float time) {                                  /* densities.h:69-132 */
-    float r = v_len(V(p.x, 0.0f, p.z));
+    const int fm = FM(P);
+    float r = v_len(0, V(p.x, 0.0f, p.z));   /* (x*x + 0*0) + z*z, unfused in both contracts */
     if (r < P->isco_radius || r > P->disk_out) return 0.0f;
     float outer = sstep(P->disk_out, P->disk_out * 0.8f, r);
     float inner = sstep(P->isco_radius, P->isco_radius + 5.0f, r);
@@ -182,15 +216,15 @@ static float dust_density(const ora_params* P, v3 p, float time) {              
     float omega = 1.0f * powf(P->isco_radius / r, 1.5f);
     float ang = phi - time * omega;
     v3 c0 = V(r * 0.8f, p.y * 15.0f, ang * 10.0f);
-    v3 w1 = V(fbm(v_scale(c0, 0.15f), 2), fbm(v_add(v_scale(c0, 0.15f), V(1, 2, 3)), 2),
-              fbm(v_add(v_scale(c0, 0.15f), V(4, 5, 6)), 2));
+    v3 w1 = V(fbm(fm, v_scale(c0, 0.15f), 2), fbm(fm, v_add(v_scale(c0, 0.15f), V(1, 2, 3)), 2),
+              fbm(fm, v_add(v_scale(c0, 0.15f), V(4, 5, 6)), 2));
     v3 c1 = v_add(c0, v_scale(w1, 3.0f));
-    v3 w2 = V(fbm(v_scale(c1, 0.4f), 2), fbm(v_add(v_scale(c1, 0.4f), V(2, 1, 0)), 2),
-              fbm(v_add(v_scale(c1, 0.4f), V(0, 3, 1)), 2));
+    v3 w2 = V(fbm(fm, v_scale(c1, 0.4f), 2), fbm(fm, v_add(v_scale(c1, 0.4f), V(2, 1, 0)), 2),
+              fbm(fm, v_add(v_scale(c1, 0.4f), V(0, 3, 1)), 2));
     v3 cf = v_add(c0, v_scale(w2, 1.5f));
     float n = 0.0f, amp = 1.0f, freq = 1.0f;
     for (int k = 0; k < 5; ++k) {
-        float nv = noise3(v_scale(cf, freq));
+        float nv = noise3(fm, v_scale(cf, freq));
         float wisp = 1.0f - fabsf(nv * 2.0f - 1.0f);
         n += wisp * amp;
         amp *= 0.5f;
@@ -198,18 +232,18 @@ static float dust_density(const ora_params* P, v3 p, float time) {              
     }
     float strands = sstep(0.4f, 0.8f, n * 0.55f);
     strands = powf(strands, 4.0f);
-    float detail = fbm(v_add(v_scale(cf, 4.0f), V(0, time * 0.5f, 0)), 2);
+    float detail = fbm(fm, v_add(v_scale(cf, 4.0f), V(0, time * 0.5f, 0)), 2);
     strands *= (0.6f + 0.4f * detail);
     return base * strands * 12.0f;
 }
 
 /* ---- post_processing.h ------------------------------------------------------------------------ */
-static void lens_distort(float* u, float* v, float k) {                                             /* post_processing.h:19-24 */
+static void lens_distort(int fm, float* u, float* v, float k) {                                     /* post_processing.h:19-24 */
     float tu = *u - 0.5f, tv = *v - 0.5f;
-    float r2 = tu * tu + tv * tv;
-    float f = 1.0f + r2 * k;
-    *u = tu * f + 0.5f;
-    *v = tv * f + 0.5f;
+    float r2 = mad2(fm, tu, tu, tv, tv);
+    float f = mad(fm, r2, k, 1.0f);
+    *u = mad(fm, tu, f, 0.5f);
+    *v = mad(fm, tv, f, 0.5f);
 }
 
 /* ---- one pixel: raymarch_kernel, src/raymarcher.cu:16-173 -------------------------------------- */
@@ -224,9 +258,10 @@ typedef struct {
 static void trace_pixel(const ora_params* P, int x, int y, int width, int height, float time, const ora_camera* cam,
                         const ora_effects* fx, const uint8_t* sky, int sky_w, int sky_h, pixel_out* o) {
     const int want_disk = (P->flags & ORA_FLAG_DISK) != 0, want_dust = (P->flags & ORA_FLAG_DUST) != 0;
+    const int fm = FM(P);
     float uvx = (float)x / width, uvy = (float)y / height;                                          /* :20 */
-    if (fx->use_lens) lens_distort(&uvx, &uvy, fx->distortion_amount);                              /* :23-25 */
-    float uc = uvx * 2.0f - 1.0f;                                                                   /* :27 */
+    if (fx->use_lens) lens_distort(fm, &uvx, &uvy, fx->distortion_amount);                              /* :23-25 */
+    float uc = uvx * 2.0f - 1.0f;                                                                   /* :27 (2*x exact: same fused) */
     float vc = uvy * 2.0f - 1.0f;                                                                   /* :28 */
     float aspect = (float)width / height;                                                           /* :29 */
     uc *= aspect;                                                                                   /* :30 */
@@ -234,14 +269,15 @@ static void trace_pixel(const ora_params* P, int x, int y, int width, int height
     v3 R = V(cam->right[0], cam->right[1], cam->right[2]);
     v3 U = V(cam->up[0], cam->up[1], cam->up[2]);
     v3 p = V(cam->pos[0], cam->pos[1], cam->pos[2]);                                                /* :32 */
-    v3 vel = v_unit(v_add(F, v_add(v_scale(R, uc), v_scale(U, vc))));                               /* :33-34 */
+    v3 vel = v_unit(fm, V(mad2(fm, R.x, uc, U.x, vc) + F.x, mad2(fm, R.y, uc, U.y, vc) + F.y,
+                          mad2(fm, R.z, uc, U.z, vc) + F.z));                                        /* :33-34 */
 
     float I[3] = {0, 0, 0}, T = 1.0f;                                                               /* :36-37 */
     int captured = 0, touched = 0, steps = 0, it;
     uint32_t n_disk = 0, n_dust = 0, n_dense = 0;
     for (it = 0; it < P->max_steps; ++it) {                                                         /* :41 */
         v3 q = v_sub(p, V(0.0f, 0.0f, 0.0f));                                                       /* :42 */
-        float r2 = v_dot(q, q);
+        float r2 = norm2_loop(fm, q);
         float r = sqrtf(r2);                                                                        /* :44 */
         if (r < P->event_horizon * 1.01f) { captured = 1; T = 0.0f; break; }                        /* :47-51 */
         float h = P->step_size;                                                                     /* :54 */
@@ -275,26 +311,26 @@ static void trace_pixel(const ora_params* P, int x, int y, int width, int height
                     float light = 0.5f + 3.0f * powf(P->isco_radius / fmaxf(r, P->isco_radius), 1.2f);
                     float J = dc * P->cloud_luminosity * light;
                     float sh = sstep(0.7f, 1.3f, g);
-                    e[0] += 0.60f * J * mixf(1.2f, 0.8f, sh);
-                    e[1] += 0.65f * J * mixf(0.8f, 1.1f, sh);
-                    e[2] += 0.80f * J * mixf(0.6f, 1.4f, sh);
+                    e[0] += 0.60f * J * mixf(fm, 1.2f, 0.8f, sh);
+                    e[1] += 0.65f * J * mixf(fm, 0.8f, 1.1f, sh);
+                    e[2] += 0.80f * J * mixf(fm, 0.6f, 1.4f, sh);
                     kappa += dc * P->cloud_opacity;
                 }
                 float tau = kappa * h;                                                              /* :107 */
                 float s = expf(-tau);
                 float w = (1.0f - s) * T;
-                I[0] += e[0] * w; I[1] += e[1] * w; I[2] += e[2] * w;                               /* :111-113 */
+                I[0] = mad(fm, e[0], w, I[0]); I[1] = mad(fm, e[1], w, I[1]); I[2] = mad(fm, e[2], w, I[2]);   /* :111-113 */
                 T *= s;                                                                             /* :115 */
             }
         }
-        if (r > 250.0f && v_dot(q, vel) > 0) break;                                                 /* :120 */
+        if (r > 250.0f && v_dot(fm, q, vel) > 0) break;                                                 /* :120 */
     }
     const int exhausted = it >= P->max_steps;
 
     float bg[3] = {0, 0, 0};
     v3 d = V(0, 0, 0);
     if (!captured) {                                                                                /* :128-146 */
-        d = v_unit(vel);
+        d = v_unit(fm, vel);
         float off = fx->use_ca ? fx->ca_amount : 0.0f;
         float offs[3] = {off, 0.0f, -off};
         for (int c = 0; c < 3; ++c) {
@@ -308,7 +344,7 @@ static void trace_pixel(const ora_params* P, int x, int y, int width, int height
         }
     }
     float hdr[3];
-    for (int c = 0; c < 3; ++c) hdr[c] = I[c] + bg[c] * T;                                          /* :148-150 */
+    for (int c = 0; c < 3; ++c) hdr[c] = mad(fm, bg[c], T, I[c]);                                          /* :148-150 */
 
     memcpy(o->hdr, hdr, sizeof hdr);
     o->T = T;
@@ -321,16 +357,19 @@ static void trace_pixel(const ora_params* P, int x, int y, int width, int height
                        (exhausted ? ORA_CLSF_EXHAUSTED : 0u) | (touched ? ORA_CLSF_TOUCHED : 0u));
 
     if (fx->use_bloom) {                                                                            /* :154-157, post_processing.h:27-31 */
-        float lum = hdr[0] * 0.2126f + hdr[1] * 0.7152f + hdr[2] * 0.0722f;
+        float lum = v_dot(fm, V(hdr[0], hdr[1], hdr[2]), V(0.2126f, 0.7152f, 0.0722f));
         float b0 = 0, b1 = 0, b2 = 0;
         if (lum > fx->bloom_threshold) { b0 = hdr[0]; b1 = hdr[1]; b2 = hdr[2]; }
-        hdr[0] = hdr[0] + b0 * fx->bloom_intensity;
-        hdr[1] = hdr[1] + b1 * fx->bloom_intensity;
-        hdr[2] = hdr[2] + b2 * fx->bloom_intensity;
+        hdr[0] = mad(fm, b0, fx->bloom_intensity, hdr[0]);
+        hdr[1] = mad(fm, b1, fx->bloom_intensity, hdr[1]);
+        hdr[2] = mad(fm, b2, fx->bloom_intensity, hdr[2]);
     }
     if (fx->use_vignette) {                                                                         /* :159-161, post_processing.h:13-17 */
-        float dist = v_len(v_sub(V(uvx, uvy, 0), V(0.5f, 0.5f, 0)));
-        float vg = sstep(0.8f, 0.2f, dist * fx->vignette_intensity);
+        float dx = uvx - 0.5f, dy = uvy - 0.5f;
+        float dist = sqrtf(mad2(fm, dx, dx, dy, dy) + 0.0f);                                        /* length((dx, dy, 0)) */
+        /* smoothstep(0.8, 0.2, dist * intensity): the product is fused into the subtraction of edge0 */
+        float tt = fminf(fmaxf((fm ? fmaf(dist, fx->vignette_intensity, -0.8f) : dist * fx->vignette_intensity - 0.8f) / (0.2f - 0.8f), 0.0f), 1.0f);
+        float vg = tt * tt * (3.0f - 2.0f * tt);
         hdr[0] *= vg; hdr[1] *= vg; hdr[2] *= vg;
     }
     for (int c = 0; c < 3; ++c) {                                                                   /* :164-172 */
@@ -518,9 +557,11 @@ void ora_euler_step(const ora_params* prm, int n, float* p, float* v, const floa
 void ora_redshift(const ora_params* prm, int n, const float* q, const float* v, float* out) {
     for (int i = 0; i < n; ++i) out[i] = redshift_factor(prm, ld3(q + 3 * i), ld3(v + 3 * i));
 }
-void ora_hash31(int n, const float* p, float* out) { for (int i = 0; i < n; ++i) out[i] = hash31(ld3(p + 3 * i)); }
-void ora_noise3d(int n, const float* p, float* out) { for (int i = 0; i < n; ++i) out[i] = noise3(ld3(p + 3 * i)); }
-void ora_fbm(int n, const float* p, int octaves, float* out) { for (int i = 0; i < n; ++i) out[i] = fbm(ld3(p + 3 * i), octaves); }
+static int g_probe_fm = 0;   /* contract of the parameter-less probes */
+void ora_set_probe_contract(int fmad) { g_probe_fm = fmad != 0; }
+void ora_hash31(int n, const float* p, float* out) { for (int i = 0; i < n; ++i) out[i] = hash31(g_probe_fm, ld3(p + 3 * i)); }
+void ora_noise3d(int n, const float* p, float* out) { for (int i = 0; i < n; ++i) out[i] = noise3(g_probe_fm, ld3(p + 3 * i)); }
+void ora_fbm(int n, const float* p, int octaves, float* out) { for (int i = 0; i < n; ++i) out[i] = fbm(g_probe_fm, ld3(p + 3 * i), octaves); }
 void ora_disk_temperature(const ora_params* prm, int n, const float* r, float* out) {
     for (int i = 0; i < n; ++i) out[i] = disk_temperature(prm, r[i]);
 }

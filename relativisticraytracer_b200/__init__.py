@@ -5,7 +5,7 @@ skybox lookup, behind the reference's own launch surface.  See DESIGN.md and INT
 The package is a thin host layer over ``librrt_b200.so`` (C ABI in ``include/rrt.h``); importing it does not
 need a GPU, calling any render or probe entry point does.
 """
-from ._capi import (Band, Camera, Counters, Effects, Params, Planes, RrtError, FLAG_DISK, FLAG_DUST, CLS_CAPTURED,
+from ._capi import (Band, Camera, Counters, Effects, Params, Planes, RrtError, FLAG_DISK, FLAG_DUST, FLAG_FMAD, CLS_CAPTURED,
                     CLS_DISK_HIT, CLS_ESCAPED, CLS_MASK, CLSF_EXHAUSTED, CLSF_TOUCHED, OUT_FRAME, OUT_PACKED, LIB_PATH,
                     default_effects, default_params, effects_off)
 from .renderer import (CameraEffects, CameraState, Renderer, Sky, camera_state_from, launch_raymarch, path_clock,

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("RRT_B200_LIB") or os.path.join(PKG_DIR, "librrt_b200.
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_IO = 0, -1, -2, -3, -4, -5
 SINK_RGBA, SINK_Y4M = 0, 1
-FLAG_DISK, FLAG_DUST = 1, 2
+FLAG_DISK, FLAG_DUST, FLAG_FMAD = 1, 2, 4
 CLS_CAPTURED, CLS_DISK_HIT, CLS_ESCAPED, CLS_MASK = 0, 1, 2, 3
 CLSF_EXHAUSTED, CLSF_TOUCHED = 4, 8
 OUT_FRAME, OUT_PACKED = 0, 1
@@ -75,7 +75,7 @@ SYMBOLS = [
     "rrt_disk_density_batch", "rrt_dust_density_batch", "rrt_sky_sample_batch", "rrt_fp32_peak_probe",
     "rrt_camera_from", "rrt_path_count", "rrt_path_name", "rrt_path_num_keys", "rrt_path_duration",
     "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest",
-    "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
+    "rrt_set_probe_contract", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def load() -> C.CDLL:
     lib.rrt_path_state.argtypes = [ci, cf, P(Camera), vp]
     lib.rrt_path_clock.argtypes = [ci, cf]
     lib.rrt_path_clock.restype = cf
+    lib.rrt_set_probe_contract.argtypes = [vp, ci]
     lib.rrt_sink_open.argtypes = [C.c_char_p, ci, ci, ci, ci, P(vp)]
     lib.rrt_sink_write.argtypes = [vp, vp]
     lib.rrt_sink_frames.argtypes = [vp]

@@ -1,0 +1,460 @@
+// rrt_kernel.cuh -- the render kernel (one 8x4-pixel tile per persistent warp), its per-ray helpers and the
+// function-level probe kernels.  Compiled TWICE, once per rounding contract (include/rrt_device.cuh):
+//   rrt_b200.cu   RRT_FMAD = 0, nvcc -fmad=false   -> rrt_kernels_strict()
+//   rrt_fmad.cu   RRT_FMAD = 1, nvcc -fmad=true    -> rrt_kernels_fmad()
+// Everything with device code sits in an anonymous namespace (internal linkage per translation unit); the
+// plain-data types both units and the host code share are in namespace rrtk.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rrt.h"
+#include "../../include/rrt_device.cuh"
+
+namespace rrtk {
+using rrt::Consts;
+
+struct FrameArgs {
+    Consts C;
+    rrt_camera cam;
+    rrt_effects fx;
+    float time;
+    int w, h;
+    int band_rank, band_nranks, band_group, local_rows;
+    int out_layout;
+    uchar4* out;
+    rrt_planes planes;
+    cudaTextureObject_t sky;
+    unsigned long long* counters;  // rrt_counters, 8 x u64
+    unsigned int* ticket;          // tile ticket for this launch
+};
+
+// kernels of one rounding contract
+struct KernelSet {
+    void (*render[2][2])(const FrameArgs);  // [spin != 0][media]
+    void (*acc)(Consts, int, const float*, const float*, float*);
+    void (*rk4)(Consts, int, float*, float*, const float*);
+    void (*euler)(Consts, int, float*, float*, const float*);
+    void (*redshift)(Consts, int, const float*, const float*, float*);
+    void (*hash31)(int, const float*, float*);
+    void (*noise3d)(int, const float*, float*);
+    void (*fbm)(int, const float*, int, float*);
+    void (*disk_temp)(Consts, int, const float*, float*);
+    void (*disk_density)(Consts, int, const float*, float, float*);
+    void (*dust_density)(Consts, int, const float*, float, float*);
+};
+const KernelSet* rrt_kernels_strict();
+const KernelSet* rrt_kernels_fmad();
+}  // namespace rrtk
+
+using rrt::Consts;
+using rrt::V3;
+using rrt::mk;
+using rrtk::FrameArgs;
+
+namespace {
+
+
+
+constexpr int kTileW = 8, kTileH = 4;  // one warp = 8x4 pixels
+constexpr int kBlock = 128;
+#ifndef RRT_MIN_BLOCKS
+#define RRT_MIN_BLOCKS 1
+#endif
+
+struct RayResult {
+    float hdr[3], T, I[3];
+    V3 d, p, v;
+    float uvx, uvy;
+    int steps;
+    unsigned n_disk, n_dust, n_dense;
+    bool captured, touched, exhausted;
+};
+
+// General-domain RK4 step (guarded div/sqrt, r < acc_rmin select): the rarely taken fallback of the loop.
+struct PV {
+    V3 p, v;
+};
+template <bool SPIN>
+__device__ __noinline__ PV rk4_step_general(const Consts& C, V3 p, V3 v, float h, float hh, float h6) {
+    const float r2 = rrt::norm2_loop(p);
+    rrt::rk4_step<SPIN>(C, p, v, h, hh, h6, r2, sqrtf(r2));
+    return PV{p, v};
+}
+
+// One in-zone sample of the participating media: densities at the PRE-step position, redshift with the
+// POST-step velocity, emission colour and the step transmittance (reference raymarcher.cu:67-108).  Kept
+// out of line so the vacuum step loop stays a few KB of straight-line FMA code in the instruction cache.
+struct MediaOut {
+    float er, eg, eb, s;
+    int dense;
+};
+// Emission colour and step transmittance of one sample given both densities (reference :71-108).
+__device__ __noinline__ MediaOut media_final(const Consts& C, V3 q, V3 v, float r, float h, float dd, float dc) {
+    MediaOut o = {0.f, 0.f, 0.f, 1.0f, 0};
+    if (dd > 0.001f || dc > 0.001f) {                                                     // :71
+        o.dense = 1;
+        float er = 0.f, eg = 0.f, eb = 0.f, kappa = 0.f;
+        const float g = rrt::redshift(C, q, v);  // same arguments in both branches (:77, :92)
+        if (dd > 0.001f) {                                                                // :76-88
+            float Tk = rrt::disk_temperature(C, r);
+            float tn = rrt::t_powf(Tk / C.disk_temp_ref, 0.5f);
+            float bol = rrt::t_powf(g, 4.0f) * tn * dd * C.disk_luminosity;
+            float ct = g * rrt::t_powf(Tk / C.disk_temp_ref, 0.4f) * 2.5f;
+            er += 1.0f * bol;
+            eg += fminf(0.25f, 0.12f * ct) * bol;
+            eb += fmaxf(0.0f, 0.01f * (ct - 2.0f)) * bol;
+            kappa += dd * C.disk_opacity;
+        }
+        if (dc > 0.001f) {                                                                // :91-105
+            float light = 0.5f + 3.0f * rrt::t_powf(C.isco / fmaxf(r, C.isco), 1.2f);
+            float J = dc * C.cloud_luminosity * light;
+            float sh = rrt::sstep(0.7f, 1.3f, g);
+            er += 0.60f * J * rrt::mixf(1.2f, 0.8f, sh);
+            eg += 0.65f * J * rrt::mixf(0.8f, 1.1f, sh);
+            eb += 0.80f * J * rrt::mixf(0.6f, 1.4f, sh);
+            kappa += dc * C.cloud_opacity;
+        }
+        const float tau = kappa * h;                                                      // :107
+        o.s = rrt::t_expf(-tau);
+        o.er = er; o.eg = eg; o.eb = eb;
+    }
+    return o;
+}
+__device__ __forceinline__ MediaOut media_sample(const Consts& C, V3 q, V3 v, float r, float h, float time, unsigned zones) {
+    const float dd = (zones & 1u) ? rrt::disk_density(C, q, time) : 0.0f;                 // :68
+    const float dc = (zones & 2u) ? rrt::dust_density(C, q, time) : 0.0f;                 // :69
+    return media_final(C, q, v, r, h, dd, dc);
+}
+
+// image-plane coordinate of a pixel after the optional lens distortion (reference :20-25)
+__device__ __forceinline__ void pixel_uv(const FrameArgs& A, int x, int y, float& uvx, float& uvy) {
+    using namespace rrt;
+    uvx = (float)x / (float)A.w;
+    uvy = (float)y / (float)A.h;
+    if (A.fx.use_lens) {  // post_processing.h:19-24
+        const float tu = sub(uvx, 0.5f), tv = sub(uvy, 0.5f);
+        const float rr = mad2(tu, tu, tv, tv);
+        const float f = mad(rr, A.fx.distortion_amount, 1.0f);
+        uvx = mad(tu, f, 0.5f);
+        uvy = mad(tv, f, 0.5f);
+    }
+}
+
+// initial ray of a pixel given its (distorted) image-plane coordinate (reference :27-34)
+__device__ __forceinline__ V3 ray_dir_uv(const FrameArgs& A, float uvx, float uvy) {
+    using namespace rrt;
+    float uc = mad(uvx, 2.0f, -1.0f);  // :27
+    const float vc = mad(uvy, 2.0f, -1.0f);  // :28
+    const float aspect = (float)A.w / (float)A.h;
+    uc = mul(uc, aspect);  // :30
+    // forward + (right*u + up*v)
+    return unit3(mk(add(mad(A.cam.right[0], uc, mul(A.cam.up[0], vc)), A.cam.forward[0]),
+                    add(mad(A.cam.right[1], uc, mul(A.cam.up[1], vc)), A.cam.forward[1]),
+                    add(mad(A.cam.right[2], uc, mul(A.cam.up[2], vc)), A.cam.forward[2])));  // :33-34
+}
+__device__ __forceinline__ V3 ray_dir(const FrameArgs& A, int x, int y) {
+    float uvx, uvy;
+    pixel_uv(A, x, y, uvx, uvy);
+    return ray_dir_uv(A, uvx, uvy);
+}
+
+constexpr unsigned kEndCaptured = 1u, kEndTouched = 2u, kEndExhausted = 4u;
+
+// Everything after the loop for one ray: background, final assembly, planes, effects, tonemap, store
+// (reference :123-173).  (uvx, uvy) is the distorted image-plane coordinate of the pixel.
+__device__ __forceinline__ void finish_ray_inl(const FrameArgs& A, int x, int y, int ly, float uvx, float uvy, float Ir, float Ig,
+                                               float Ib, float T, V3 p, V3 v, int steps, unsigned end) {
+    using namespace rrt;
+    float bg[3] = {0.f, 0.f, 0.f};
+    V3 d = mk(0.f, 0.f, 0.f);
+    const bool captured = (end & kEndCaptured) != 0;
+    if (!captured) {
+        d = unit3(v);
+        const float off = A.fx.use_ca ? A.fx.ca_amount : 0.0f;
+        const float theta = asinf(d.y);
+        const float ty_ = 0.5f - theta / kPi;
+        const float phi0 = atan2f(d.z, d.x);
+        float4 sR = tex2D<float4>(A.sky, 0.5f + (phi0 + off) / (2.0f * kPi), ty_);
+        float4 sG = tex2D<float4>(A.sky, 0.5f + (phi0 + 0.0f) / (2.0f * kPi), ty_);
+        float4 sB = tex2D<float4>(A.sky, 0.5f + (phi0 + -off) / (2.0f * kPi), ty_);
+        bg[0] = sR.x; bg[1] = sG.y; bg[2] = sB.z;
+    }
+    float hr = mad(bg[0], T, Ir), hg = mad(bg[1], T, Ig), hb = mad(bg[2], T, Ib);  // :148-150
+    const bool touched = (end & kEndTouched) != 0, exhausted = (end & kEndExhausted) != 0;
+    const size_t pix = (size_t)y * A.w + x;
+    const uint8_t cls = (uint8_t)((captured ? RRT_CLS_CAPTURED : (touched ? RRT_CLS_DISK_HIT : RRT_CLS_ESCAPED)) |
+                                  (exhausted ? RRT_CLSF_EXHAUSTED : 0u) | (touched ? RRT_CLSF_TOUCHED : 0u));
+    if (A.planes.hdr) reinterpret_cast<float4*>(A.planes.hdr)[pix] = make_float4(hr, hg, hb, T);
+    if (A.planes.dir) reinterpret_cast<float4*>(A.planes.dir)[pix] = make_float4(d.x, d.y, d.z, 0.f);
+    if (A.planes.emis) reinterpret_cast<float4*>(A.planes.emis)[pix] = make_float4(Ir, Ig, Ib, 0.f);
+    if (A.planes.pos) reinterpret_cast<float4*>(A.planes.pos)[pix] = make_float4(p.x, p.y, p.z, 0.f);
+    if (A.planes.vel) reinterpret_cast<float4*>(A.planes.vel)[pix] = make_float4(v.x, v.y, v.z, 0.f);
+    if (A.planes.cls) A.planes.cls[pix] = cls;
+    if (A.planes.steps) A.planes.steps[pix] = steps;
+    if (!A.out) return;
+    if (A.fx.use_bloom) {  // :154-157, post_processing.h:27-31
+        const float lum = dot3(mk(hr, hg, hb), mk(0.2126f, 0.7152f, 0.0722f));
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (lum > A.fx.bloom_threshold) { b0 = hr; b1 = hg; b2 = hb; }
+        hr = mad(b0, A.fx.bloom_intensity, hr);
+        hg = mad(b1, A.fx.bloom_intensity, hg);
+        hb = mad(b2, A.fx.bloom_intensity, hb);
+    }
+    if (A.fx.use_vignette) {  // :159-161, post_processing.h:13-17; smoothstep(0.8, 0.2, d * intensity), math_utils.h:45-48
+        const float dx = sub(uvx, 0.5f), dy = sub(uvy, 0.5f);
+        const float dist = sqrtf(add(mad2(dx, dx, dy, dy), 0.0f));
+        const float t = fminf(fmaxf(msub(dist, A.fx.vignette_intensity, 0.8f) / (0.2f - 0.8f), 0.0f), 1.0f);
+        const float vg = mul(mul(t, t), sub(3.0f, mul(2.0f, t)));
+        hr = mul(hr, vg); hg = mul(hg, vg); hb = mul(hb, vg);
+    }
+    const float o_r = 1.0f - expf(mul(-hr, A.C.exposure));  // :164-166
+    const float o_g = 1.0f - expf(mul(-hg, A.C.exposure));
+    const float o_b = 1.0f - expf(mul(-hb, A.C.exposure));
+    const uchar4 px = make_uchar4((unsigned char)(o_r * 255), (unsigned char)(o_g * 255), (unsigned char)(o_b * 255), 255);
+    if (A.out_layout == RRT_OUT_FRAME) A.out[(size_t)(A.h - 1 - y) * A.w + x] = px;  // :168
+    else A.out[(size_t)ly * A.w + x] = px;
+}
+// out-of-line copy for the kernels that finalise rays one at a time from several places
+__device__ __noinline__ void finish_ray(const FrameArgs& A, int x, int y, int ly, float Ir, float Ig, float Ib, float T, V3 p,
+                                        V3 v, int steps, unsigned end) {
+    float uvx, uvy;
+    pixel_uv(A, x, y, uvx, uvy);
+    finish_ray_inl(A, x, y, ly, uvx, uvy, Ir, Ig, Ib, T, p, v, steps, end);
+}
+
+// One ray: reference raymarch_kernel lines 20-150.
+template <bool SPIN, bool MEDIA>
+__device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayResult& R) {
+    const Consts& C = A.C;
+    float uvx, uvy;
+    pixel_uv(A, x, y, uvx, uvy);                                       // :20-25
+    V3 p = mk(A.cam.pos[0], A.cam.pos[1], A.cam.pos[2]);
+    V3 v = ray_dir_uv(A, uvx, uvy);                                    // :27-34
+
+    float Ir = 0.f, Ig = 0.f, Ib = 0.f, T = 1.0f;
+    bool captured = false, touched = false, escaped = false;
+    int it = 0;
+    unsigned n_disk = 0, n_dust = 0, n_dense = 0;
+    const int max_steps = C.max_steps;
+    const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
+    // Domain of the branch-free div/sqrt (rrt_device.cuh): a ray that starts absurdly far out takes the
+    // general path for its whole life.  Uniform per launch in practice (depends on the camera only).
+    const bool fast_ok = rrt::dot3(p, p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
+    const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
+    // one compare per step for "redo with the general code": smallest stage radius below acc_rmin (or NaN), or
+    // the whole ray outside the fast domain (+inf: every step is redone)
+    const float redo_below = fast_ok ? C.acc_rmin : __int_as_float(0x7f800000);
+    // Two-level loop.  The inner loop holds what (nearly) every step needs -- the branch-free RK4 step and, in
+    // lock-step for the lanes that are inside a medium, the out-of-line media sample -- and nothing else; the
+    // general-domain redo of a step (practically never taken) is done by the outer loop, which then re-enters,
+    // so its call does not cost the hot loop registers or convergence barriers.  `it` counts executed
+    // integrate_rk4 calls on every path.
+    auto fold = [&](const MediaOut& m) {                                                      // :71, :107-115
+        if (m.dense) {
+            touched = true;
+            ++n_dense;
+            const float wgt = rrt::mul(rrt::sub(1.0f, m.s), T);                               // :109
+            Ir = rrt::mad(m.er, wgt, Ir); Ig = rrt::mad(m.eg, wgt, Ig); Ib = rrt::mad(m.eb, wgt, Ib);   // :111-113
+            T = rrt::mul(T, m.s);                                                             // :115
+        }
+    };
+    enum : int { kRanOut = 0, kCaptured = 1, kEscaped = 2, kRedo = 3 };
+    for (;;) {
+        int ev = kRanOut;
+        V3 q = p, v_in = v;   // pre-step state: media and the escape test use q (:68-69, :120)
+        float r = 0.0f, h = C.h[0], hh = C.hh[0], h6 = C.h6[0];
+        unsigned zones = 0;
+#pragma unroll 1
+        while (it < max_steps) {                                                              // :41
+            const float r2 = rrt::norm2_loop(p);
+            r = rrt::sqrt_rn_fast(r2);                                                        // :44
+            if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
+            h = C.h[0]; h6 = C.h6[0];
+            unsigned z = 0;
+            if (r < zone_rmax) {  // 3/4 of all steps are outside every zone: one compare for them
+                const bool near_bh = r < 18.0f;                                               // :56
+                const bool disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;       // :57
+                const bool dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;       // :58
+                const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));           // :60-62
+                h = C.h[zi];
+                h6 = C.h6[zi];
+                if (MEDIA) z = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);   // :67
+            }
+            zones = z;
+            hh = h * 0.5f;  // exact
+            q = p;
+            v_in = v;
+            const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);           // :64
+            if (!(rmin >= redo_below)) { ev = kRedo; break; }
+            ++it;
+            if (MEDIA && z) {
+                n_disk += z & 1u;
+                n_dust += z >> 1;
+                fold(media_sample(C, q, v, r, h, A.time, z));
+            }
+            if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { ev = kEscaped; break; }               // :120
+        }
+        if (ev == kRedo) {
+            // outside the branch-free domain, or geodesics.h:33 can fire: redo this step with the general code
+            const PV s = rk4_step_general<SPIN>(C, q, v_in, h, hh, h6);
+            p = s.p; v = s.v;
+            ++it;
+            if (MEDIA && zones) {
+                n_disk += zones & 1u;
+                n_dust += zones >> 1;
+                fold(media_sample(C, q, v, r, h, A.time, zones));
+            }
+            if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { escaped = true; break; }              // :120
+            continue;
+        }
+        if (ev == kCaptured) { captured = true; T = 0.0f; }
+        escaped = ev == kEscaped;
+        break;
+    }
+    R.exhausted = !captured && !escaped;  // the for loop ran out (:41)
+    R.steps = it;
+    R.captured = captured;
+    R.touched = touched;
+    R.n_disk = n_disk; R.n_dust = n_dust; R.n_dense = n_dense;
+    R.p = p; R.v = v; R.T = T;
+    R.I[0] = Ir; R.I[1] = Ig; R.I[2] = Ib;
+    R.uvx = uvx; R.uvy = uvy;
+}
+
+template <bool SPIN, bool MEDIA>
+__global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ FrameArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int ntx = (A.w + kTileW - 1) / kTileW;
+    const int nty = (A.local_rows + kTileH - 1) / kTileH;
+    const unsigned ntiles = (unsigned)(ntx * nty);
+    unsigned long long c_steps = 0, c_disk = 0, c_dust = 0, c_dense = 0;
+    unsigned c_cap = 0, c_esc = 0, c_exh = 0, c_touch = 0;
+
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(A.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        // Tile rows are handed out from the image centre outwards: the rows that cross the hole and the
+        // disk are the expensive ones, so they start first and the cheap sky rows fill the tail of the launch.
+        const int tx = (int)(tile % (unsigned)ntx), k = (int)(tile / (unsigned)ntx);
+        const int c = nty >> 1, m = min(c, nty - 1 - c);
+        int ty;
+        if (k <= 2 * m) ty = (k & 1) ? c + ((k + 1) >> 1) : c - (k >> 1);
+        else ty = (c > nty - 1 - c) ? (c - m - 1) - (k - (2 * m + 1)) : (c + m + 1) + (k - (2 * m + 1));
+        const int x = tx * kTileW + (lane & (kTileW - 1));
+        const int ly = ty * kTileH + (lane >> 3);
+        if (x >= A.w || ly >= A.local_rows) continue;
+        const int grp = ly / A.band_group;
+        const int y = (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
+        if (y >= A.h) continue;
+
+        RayResult R;
+        trace_ray<SPIN, MEDIA>(A, x, y, R);
+
+        finish_ray_inl(A, x, y, ly, R.uvx, R.uvy, R.I[0], R.I[1], R.I[2], R.T, R.p, R.v, R.steps,
+                       (R.captured ? kEndCaptured : 0u) | (R.touched ? kEndTouched : 0u) | (R.exhausted ? kEndExhausted : 0u));
+        c_steps += (unsigned)R.steps;
+        c_disk += R.n_disk; c_dust += R.n_dust; c_dense += R.n_dense;
+        c_cap += R.captured; c_exh += R.exhausted; c_esc += (!R.captured && !R.exhausted); c_touch += R.touched;
+    }
+
+    // one set of atomics per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_steps += __shfl_xor_sync(0xffffffffu, c_steps, o);
+        c_disk += __shfl_xor_sync(0xffffffffu, c_disk, o);
+        c_dust += __shfl_xor_sync(0xffffffffu, c_dust, o);
+        c_dense += __shfl_xor_sync(0xffffffffu, c_dense, o);
+        c_cap += __shfl_xor_sync(0xffffffffu, c_cap, o);
+        c_esc += __shfl_xor_sync(0xffffffffu, c_esc, o);
+        c_exh += __shfl_xor_sync(0xffffffffu, c_exh, o);
+        c_touch += __shfl_xor_sync(0xffffffffu, c_touch, o);
+    }
+    if (lane == 0 && A.counters) {
+        atomicAdd(A.counters + 0, c_steps);
+        atomicAdd(A.counters + 1, c_disk);
+        atomicAdd(A.counters + 2, c_dust);
+        atomicAdd(A.counters + 3, c_dense);
+        atomicAdd(A.counters + 4, (unsigned long long)c_cap);
+        atomicAdd(A.counters + 5, (unsigned long long)c_esc);
+        atomicAdd(A.counters + 6, (unsigned long long)c_exh);
+        atomicAdd(A.counters + 7, (unsigned long long)c_touch);
+    }
+}
+
+// ---- probe kernels ---------------------------------------------------------------------------------
+__device__ __forceinline__ V3 ld3(const float* a, int i) { return mk(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+__device__ __forceinline__ void st3(float* a, int i, V3 v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
+
+__global__ void k_acc(Consts C, int n, const float* q, const float* v, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st3(out, i, C.spin_a != 0.0f ? rrt::geodesic_acc<true>(C, ld3(q, i), ld3(v, i))
+                                            : rrt::geodesic_acc<false>(C, ld3(q, i), ld3(v, i)));
+}
+__global__ void k_rk4(Consts C, int n, float* p, float* v, const float* h) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 pp = ld3(p, i), vv = ld3(v, i);
+    float hi = h[i], r2 = rrt::norm2_loop(pp);
+    if (C.spin_a != 0.0f) rrt::rk4_step<true>(C, pp, vv, hi, hi * 0.5f, hi / 6.0f, r2, sqrtf(r2));
+    else rrt::rk4_step<false>(C, pp, vv, hi, hi * 0.5f, hi / 6.0f, r2, sqrtf(r2));
+    st3(p, i, pp);
+    st3(v, i, vv);
+}
+__global__ void k_euler(Consts C, int n, float* p, float* v, const float* h) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 pp = ld3(p, i), vv = ld3(v, i);
+    if (C.spin_a != 0.0f) rrt::euler_step<true>(C, pp, vv, h[i]);
+    else rrt::euler_step<false>(C, pp, vv, h[i]);
+    st3(p, i, pp);
+    st3(v, i, vv);
+}
+__global__ void k_redshift(Consts C, int n, const float* q, const float* v, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::redshift(C, ld3(q, i), ld3(v, i));
+}
+__global__ void k_hash31(int n, const float* p, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::hash31(ld3(p, i));
+}
+__global__ void k_noise3d(int n, const float* p, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::noise3d(ld3(p, i));
+}
+__global__ void k_fbm(int n, const float* p, int oct, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::fbm_rt(ld3(p, i), oct);
+}
+__global__ void k_disk_temp(Consts C, int n, const float* r, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::disk_temperature(C, r[i]);
+}
+__global__ void k_disk_density(Consts C, int n, const float* q, float time, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::disk_density(C, ld3(q, i), time);
+}
+__global__ void k_dust_density(Consts C, int n, const float* q, float time, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rrt::dust_density(C, ld3(q, i), time);
+}
+__global__ void k_sky(cudaTextureObject_t sky, int n, const float* tx, const float* ty, float4* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex2D<float4>(sky, tx[i], ty[i]);
+}
+
+const rrtk::KernelSet kKernelSet = {
+    {{render_kernel<false, false>, render_kernel<false, true>}, {render_kernel<true, false>, render_kernel<true, true>}},
+    k_acc, k_rk4, k_euler, k_redshift, k_hash31, k_noise3d, k_fbm, k_disk_temp, k_disk_density, k_dust_density,
+};
+}  // namespace
+
+namespace rrtk {
+#if RRT_FMAD
+const KernelSet* rrt_kernels_fmad() { return &kKernelSet; }
+#else
+const KernelSet* rrt_kernels_strict() { return &kKernelSet; }
+#endif
+}  // namespace rrtk

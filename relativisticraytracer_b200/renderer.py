@@ -198,6 +198,10 @@ class Renderer:
         self._check(self._lib.rrt_fp32_peak_probe(self._ctx, int(iters), C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
+    def set_probe_contract(self, fmad: bool) -> None:
+        """Rounding contract of hash31 / noise3d / fbm (the probes without a parameter block)."""
+        self._check(self._lib.rrt_set_probe_contract(self._ctx, 1 if fmad else 0))
+
     def exact_math_selftest(self, seed: int = 1, n: int = 1 << 30):
         """(div mismatches, sqrt mismatches) of the loop's branch-free div/sqrt vs the IEEE intrinsics."""
         a, b = C.c_uint64(), C.c_uint64()
