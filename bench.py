@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--flags", type=int, default=3, help="experiment only: media flags (3 = disk+dust = the headline workload)")
     ap.add_argument("--camera", default="C0", help="experiment only: C0 (headline) .. C3")
+    ap.add_argument("--strict", action="store_true",
+                    help="experiment only: clear RRT_FLAG_FMAD (unfused arithmetic, the twin of the reference headers on a host) "
+                         "instead of the default contract, the arithmetic of the reference's own CUDA build")
     ap.add_argument("--depth", type=int, default=2, help="frames in flight in the timed sequence (1 = one at a time)")
     ap.add_argument("--workload", default="frame", choices=["frame", "path"],
                     help="frame (default, the headline: one 4K frame cut into row bands) or path (BASELINE config 5: "
@@ -242,7 +245,7 @@ def main():
 
     r = rrt.Renderer(dev)
     sky = r.create_sky(rrt.procedural_sky(4096, 2048))
-    prm = rrt.default_params(spin_a=SPIN, flags=args.flags)
+    prm = rrt.default_params(spin_a=SPIN, flags=args.flags | (0 if args.strict else rrt.FLAG_FMAD))
     if args.workload == "path":
         run_path_workload(args, r, sky, prm, world, rank, dev)
         if world > 1:

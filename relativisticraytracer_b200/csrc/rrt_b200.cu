@@ -768,7 +768,7 @@ void rrt_default_params(rrt_params* o) {  // include/config.h
     o->step_size = 0.3f;
     o->disk_temp_ref = 1.5e7f;
     o->max_steps = 2000;
-    o->flags = RRT_FLAG_DISK | RRT_FLAG_DUST;
+    o->flags = RRT_FLAG_DISK | RRT_FLAG_DUST | RRT_FLAG_FMAD;  // both media; the rounding contract of the reference's CUDA build
 }
 
 void rrt_default_effects(rrt_effects* o) {  // camera_settings.h:5-16

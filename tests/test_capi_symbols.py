@@ -45,7 +45,7 @@ def test_struct_layouts_and_defaults(built):
     p = _capi.default_params()
     # include/config.h
     assert (p.spin_a, p.event_horizon, p.isco_radius, p.disk_out, p.max_steps) == (0.0, 2.0, 10.0, 25.0, 2000)
-    assert abs(p.step_size - 0.3) < 1e-7 and abs(p.disk_temp_ref - 1.5e7) < 1 and p.flags == 3
+    assert abs(p.step_size - 0.3) < 1e-7 and abs(p.disk_temp_ref - 1.5e7) < 1 and p.flags == 7   # disk | dust | RRT_FLAG_FMAD
     e = _capi.default_effects()
     # camera_settings.h:5-16
     assert (e.use_bloom, e.use_vignette, e.use_ca, e.use_lens) == (1, 1, 0, 1)

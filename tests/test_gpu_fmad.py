@@ -36,7 +36,7 @@ def test_fmad_rhs_and_integrators_match_twin(gpu, ora, spin):
         p2, v2 = ora.euler_step(po, q, v, h)
         assert bits_equal(p1, p2) and bits_equal(v1, v2)
     # and the fused schedule really is a different rounding from the strict one
-    ps, _ = gpu.rk4_step(rrt.default_params(spin_a=spin), q, v, np.float32(0.3))
+    ps, _ = gpu.rk4_step(rrt.default_params(spin_a=spin, flags=3), q, v, np.float32(0.3))
     pf, _ = gpu.rk4_step(pg, q, v, np.float32(0.3))
     assert not np.array_equal(ps, pf)
 
@@ -94,31 +94,54 @@ def test_fmad_geodesic_only_and_effects(gpu, ora, sky_smooth):
     assert d.max() <= 1 and np.mean(d > 0) < 0.02
 
 
-@pytest.mark.parametrize("cam", ["C0", "C1", "C3"])
-@pytest.mark.parametrize("spin", [0.0, 0.99])
-def test_fmad_bytes_equal_reference_cuda_kernel(gpu, sky_small, cam, spin):
-    """Against the reference's own CUDA kernel (unmodified src/raymarcher.cu, nvcc defaults, same GPU): every
-    pixel whose ray never touched a medium is byte-identical; pixels that did stay within one count (there the
-    density code is left to nvcc's own fusion in both builds, which need not coincide)."""
+def _ours_vs(gpu, sky_np, ref_rgba, cam, spin, w, h):
     import relativisticraytracer_b200 as rrt
     import torch
-    from oracle import RefCuda
-    if not RefCuda.available():
-        pytest.skip("oracle/_ref/libref_cuda.so not built (reference tree absent at build time)")
-    w, h = 320, 180
-    pos, yaw, pitch = CAMERAS[cam]
-    cg = rrt.camera_state_from(pos, yaw, pitch)
-    fx = rrt.default_effects()
-    ref_rgba, _, _ = RefCuda().render(spin, cg, fx, sky_small, 1.0, w, h)
-    sky = gpu.create_sky(sky_small)
-    planes = gpu.alloc_planes(w, h, names=("cls", "steps"))
-    out = gpu.render(rrt.default_params(spin_a=spin, flags=3 | FMAD), cg, fx, sky, 1.0, w, h, planes=planes)
+    sky = gpu.create_sky(sky_np)
+    planes = gpu.alloc_planes(w, h, names=("cls",))
+    out = gpu.render(rrt.default_params(spin_a=spin, flags=3 | FMAD), rrt.camera_state_from(*CAMERAS[cam]),
+                     rrt.default_effects(), sky, 1.0, w, h, planes=planes)
     torch.cuda.synchronize()
     ours = out.cpu().numpy()
     cls = planes["cls"].cpu().numpy()[::-1]            # planes are [y][x]; the uchar4 frame is row-flipped (:168)
     sky.close()
     untouched = (cls & rrt.CLSF_TOUCHED) == 0
     diff = np.abs(ours.astype(int) - ref_rgba.astype(int)).max(axis=-1)
+    return untouched, diff
+
+
+@pytest.mark.parametrize("cam", ["C0", "C1", "C2", "C3"])
+@pytest.mark.parametrize("spin", [0.0, 0.99])
+def test_fmad_bytes_equal_reference_cuda_kernel(gpu, sky_small, cam, spin):
+    """Against the reference's own CUDA kernel (unmodified src/raymarcher.cu, nvcc defaults, same GPU): every
+    pixel whose ray never touched a medium is byte-identical; of the pixels that did (there the density code is
+    left to nvcc's own fusion in both builds, which need not coincide) at most a handful differ, by one count.
+    Measured at 960x540 with the 4096x2048 star-field sky, 8 camera/spin cases (tools/refcuda_census.py):
+    0 of 3.66 M untouched and 2 of 0.49 M touched pixels differ."""
+    import relativisticraytracer_b200 as rrt
+    from oracle import RefCuda
+    if not RefCuda.available():
+        pytest.skip("oracle/_ref/libref_cuda.so not built (reference tree absent at build time)")
+    w, h = 320, 180
+    ref_rgba, _, _ = RefCuda().render(spin, rrt.camera_state_from(*CAMERAS[cam]), rrt.default_effects(), sky_small, 1.0, w, h)
+    untouched, diff = _ours_vs(gpu, sky_small, ref_rgba, cam, spin, w, h)
     assert untouched.mean() > 0.3
     assert diff[untouched].max() == 0, f"{int((diff[untouched] > 0).sum())} untouched pixels differ from the reference kernel"
-    assert diff[~untouched].max() <= 1, f"touched pixels differ by up to {diff[~untouched].max()} counts"
+    assert diff[~untouched].max() <= 1 and (diff[~untouched] > 0).sum() <= 3, \
+        f"{int((diff[~untouched] > 0).sum())} touched pixels differ, by up to {diff[~untouched].max()} counts"
+
+
+@pytest.mark.parametrize("cam", ["C0", "C1", "C2", "C3"])
+@pytest.mark.parametrize("tag,spin", [("a000", 0.0), ("a099", 0.99)])
+def test_fmad_bytes_equal_committed_reference_cuda_frames(gpu, sky_small, cam, tag, spin):
+    """Same check against frames of the reference kernel committed under tests/golden/ (generated on a B200 by
+    tools/make_golden_refcuda.py), so the pin does not depend on the reference tree being present."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "refcuda_frames.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/refcuda_frames.npz not generated yet")
+    ref_rgba = np.load(path)[f"{cam}_{tag}"]
+    h, w = ref_rgba.shape[:2]
+    untouched, diff = _ours_vs(gpu, sky_small, ref_rgba, cam, spin, w, h)
+    assert diff[untouched].max() == 0
+    assert diff[~untouched].max() <= 1 and (diff[~untouched] > 0).sum() <= 3

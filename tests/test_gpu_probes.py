@@ -19,6 +19,8 @@ def bits_equal(a, b):
 
 
 def params_pair(rrt, ora, **kw):
+    """strict contract (flags = media only): the twin of the reference headers on the host"""
+    kw.setdefault("flags", 3)
     return rrt.default_params(**kw), ora.default_params(**kw)
 
 
@@ -101,7 +103,7 @@ def test_redshift_close(gpu, ora, spin):
 def test_disk_temperature_close(gpu, ora):
     import relativisticraytracer_b200 as rrt
     r = np.concatenate([np.linspace(5, 40, 2000), [9.999, 10.0, 10.001]]).astype(np.float32)
-    a, b = gpu.disk_temperature(rrt.default_params(), r), ora.disk_temperature(ora.default_params(), r)
+    a, b = gpu.disk_temperature(rrt.default_params(flags=3), r), ora.disk_temperature(ora.default_params(), r)
     assert np.array_equal(a == 0, b == 0)
     np.testing.assert_allclose(a, b, rtol=TRANSCENDENTAL_RTOL)
 
@@ -110,7 +112,7 @@ def test_disk_temperature_close(gpu, ora):
 def test_disk_density_close(gpu, ora, time):
     import relativisticraytracer_b200 as rrt
     q = disk_points(seed=40)
-    a, b = gpu.disk_density(rrt.default_params(), q, time), ora.disk_density(ora.default_params(), q, time)
+    a, b = gpu.disk_density(rrt.default_params(flags=3), q, time), ora.disk_density(ora.default_params(), q, time)
     assert np.array_equal(a == 0, b == 0)            # range gate is exact arithmetic
     # density = env * (0.02 + 5c): compare against the scale of the value plus the noise floor of c
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
@@ -122,7 +124,7 @@ def test_disk_density_close(gpu, ora, time):
 def test_dust_density_close(gpu, ora, time):
     import relativisticraytracer_b200 as rrt
     q = disk_points(seed=41)
-    a, b = gpu.dust_density(rrt.default_params(), q, time), ora.dust_density(ora.default_params(), q, time)
+    a, b = gpu.dust_density(rrt.default_params(flags=3), q, time), ora.dust_density(ora.default_params(), q, time)
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
     # a sample sitting within an ulp of the base<0.001 early-out may flip to exactly 0 on one side
     assert np.mean((a == 0) != (b == 0)) < 1e-3
