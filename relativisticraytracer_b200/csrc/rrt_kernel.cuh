@@ -61,6 +61,13 @@ constexpr int kBlock = 128;
 #ifndef RRT_MIN_BLOCKS
 #define RRT_MIN_BLOCKS 1
 #endif
+// The media variant of the render kernel is asked to fit 6 CTAs (24 warps) per SM, i.e. <= 80 registers: the
+// out-of-line media code stalls on libdevice call chains and MUFU latency, and six warps per scheduler hide
+// that better than the four the unconstrained 109-register build gets (4K C0 78.5 -> 76.2 ms, C3 147.6 -> 135.4;
+// 7 and 8 CTAs are no better).  The geodesic-only variant needs ~72 registers anyway.
+#ifndef RRT_MIN_BLOCKS_MEDIA
+#define RRT_MIN_BLOCKS_MEDIA 6
+#endif
 
 struct RayResult {
     float hdr[3], T, I[3];
@@ -265,10 +272,13 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
         V3 q = p, v_in = v;   // pre-step state: media and the escape test use q (:68-69, :120)
         float r = 0.0f, h = C.h[0], hh = C.hh[0], h6 = C.h6[0];
         unsigned zones = 0;
+        // The loop is rotated: |p| of the NEXT iteration's header (:43-44) is computed right after the step, so
+        // its multiply -> rsqrt -> refine chain overlaps the escape test and the loop bookkeeping instead of
+        // standing alone at the top of every iteration (it was ~20 % of the stall samples there).
+        float r2 = rrt::norm2_loop(p);
+        r = rrt::sqrt_rn_fast(r2);                                                            // :44
 #pragma unroll 1
         while (it < max_steps) {                                                              // :41
-            const float r2 = rrt::norm2_loop(p);
-            r = rrt::sqrt_rn_fast(r2);                                                        // :44
             if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
             h = C.h[0]; h6 = C.h6[0];
             unsigned z = 0;
@@ -288,12 +298,16 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);           // :64
             if (!(rmin >= redo_below)) { ev = kRedo; break; }
             ++it;
+            const float r2_next = rrt::norm2_loop(p);
+            const float r_next = rrt::sqrt_rn_fast(r2_next);
             if (MEDIA && z) {
                 n_disk += z & 1u;
                 n_dust += z >> 1;
                 fold(media_sample(C, q, v, r, h, A.time, z));
             }
             if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { ev = kEscaped; break; }               // :120
+            r2 = r2_next;
+            r = r_next;
         }
         if (ev == kRedo) {
             // outside the branch-free domain, or geodesics.h:33 can fire: redo this step with the general code
@@ -323,7 +337,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 }
 
 template <bool SPIN, bool MEDIA>
-__global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ FrameArgs A) {
+__global__ void __launch_bounds__(kBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ FrameArgs A) {
     const int lane = threadIdx.x & 31;
     const int ntx = (A.w + kTileW - 1) / kTileW;
     const int nty = (A.local_rows + kTileH - 1) / kTileH;
