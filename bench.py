@@ -33,7 +33,7 @@ TIME = 1.0
 BAND_GROUP = 8
 FLOP_PER_STEP = 218.0          # algorithmic FLOP of one RK4 geodesic step, a != 0
 FP32_THEORETICAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4, at clocks.max.sm
-CPU_SAMPLE = (640, 360)        # bounded CPU sample of the same camera / parameters
+CPU_SAMPLE = (1280, 720)       # bounded CPU sample of the same camera / parameters (~5 s on 16 host cores)
 WORKLOAD = "3840x2160 Kerr a=0.99 volumetric (disk+dust) frame, camera C0, cyclic 8-row bands over N GPUs"
 
 
@@ -379,7 +379,10 @@ def main():
     achieved_tflops = FLOP_PER_STEP * kern_steps_per_s / 1e12
     roofline = {
         "bound": "fp32_fma", "achieved": achieved_tflops, "peak": fp32_meas, "unit": "TFLOP/s",
-        "frac": achieved_tflops / fp32_meas, "traffic": None,
+        "frac": achieved_tflops / fp32_meas,
+        # DRAM bytes of one launch from the ncu --set full capture kept under profiles/ (dram__bytes_read.sum +
+        # dram__bytes_write.sum; sky texels in, nothing else: the 33 MB frame stays in L2): the headline workload only
+        "traffic": 9.42e6 if (w, h, args.flags, args.camera, world) == (W4K, H4K, 3, "C0", 1) else None,
         "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
         "peak_theoretical": FP32_THEORETICAL_TFLOPS, "frac_of_theoretical": achieved_tflops / FP32_THEORETICAL_TFLOPS,
         "flop_per_step": FLOP_PER_STEP, "kernel": "render_kernel<spin,media>", "kernel_ms": kern_ms_per_step,
@@ -394,6 +397,8 @@ def main():
                    "width": w, "height": h, "spin_a": SPIN, "media": "disk+dust", "camera": "C0", "band_group_rows": BAND_GROUP,
                    "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) before every frame",
                    "frames_in_flight": depth,
+                   "rounding_contract": ("strict: unfused mul+add, the twin of the reference headers on a host" if args.strict else
+                                         "fmad: the FMA fusion schedule of the reference's own CUDA build (default)"),
                    "rk4_steps_per_frame": rk4_per_frame, "disk_evals_per_frame": disk_evals, "dust_evals_per_frame": dust_evals},
         "frames_per_s": 1e3 / ms_per_step,
         "latency_ms_single_frame": lat_ms_per_step,
@@ -409,7 +414,7 @@ def main():
 
     if world == 1 and not args.no_cpu_baseline:
         cw, ch = CPU_SAMPLE
-        steps_c, secs, meta = cpu_reference_run(cw, ch)
+        steps_c, secs, meta = cpu_reference_run(cw, ch, repeats=3)     # ~15 s of host work, best of 3
         line["cpu_baseline"] = {"value": steps_c / secs, "unit": "steps/s", "cores": meta["cores"], "kind": meta["kind"],
                                 "sample": meta["sample"], "seconds": secs}
     if world == 1 and not args.no_ref_cuda:

@@ -280,22 +280,33 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 #pragma unroll 1
         while (it < max_steps) {                                                              // :41
             if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
-            h = C.h[0]; h6 = C.h6[0];
             unsigned z = 0;
-            if (r < zone_rmax) {  // 3/4 of all steps are outside every zone: one compare for them
-                const bool near_bh = r < 18.0f;                                               // :56
-                const bool disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;       // :57
-                const bool dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;       // :58
-                const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));           // :60-62
-                h = C.h[zi];
-                h6 = C.h6[zi];
-                if (MEDIA) z = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);   // :67
-            }
-            zones = z;
-            hh = h * 0.5f;  // exact
+            float rmin;
             q = p;
             v_in = v;
-            const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);           // :64
+            if (!RRT_FMAD || r < zone_rmax) {
+                h = C.h[0]; h6 = C.h6[0];
+                if (r < zone_rmax) {  // one compare for the steps outside every zone
+                    const bool near_bh = r < 18.0f;                                           // :56
+                    const bool disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;   // :57
+                    const bool dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;   // :58
+                    const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));       // :60-62
+                    h = C.h[zi];
+                    h6 = C.h6[zi];
+                    if (MEDIA) z = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);   // :67
+                }
+                hh = h * 0.5f;  // exact
+                rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);                   // :64
+            } else {
+                // FMAD contract only.  3/4 of all steps are outside every zone; their step size is the same for the
+                // whole warp, so this second copy of the step takes h, h/2 and h/6 as constant-bank operands and 24 of
+                // its FFMAs read two registers instead of three.  The fused loop is bound by register-file operand
+                // bandwidth: 4K C0 75.8 -> 74.1 ms.  The strict loop is issue bound and loses 3 % to the
+                // larger code, so it keeps the single copy.
+                h = C.h[0]; hh = C.hh[0]; h6 = C.h6[0];
+                rmin = rrt::rk4_step_fast<SPIN>(C, p, v, C.h[0], C.hh[0], C.h6[0], r2, r);    // :64
+            }
+            zones = z;
             if (!(rmin >= redo_below)) { ev = kRedo; break; }
             ++it;
             const float r2_next = rrt::norm2_loop(p);
