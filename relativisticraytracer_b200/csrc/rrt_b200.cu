@@ -29,501 +29,9 @@ using rrt::V3;
 using rrt::mk;
 
 #include "rrt_kernel.cuh"
+#include "rrt_variants.cuh"   // measured alternatives to render_kernel (RRT_KERNEL_VARIANT=2, 3), strict contract only
 
 namespace {
-
-// =====================================================================================================
-// render_kernel2 (opt-in, RRT_KERNEL_VARIANT=2; bit-identical output, same speed as render_kernel on B200 --
-// see profiles/r1_history.md "packed f32x2 experiment"):
-// two rays per thread in packed f32x2 registers (see include/rrt_device.cuh, "Packed FP32").
-// One warp = a 16x4-pixel tile; thread (lx, ly) owns pixels (2*lx, ly) and (2*lx+1, ly) of the tile.  The
-// two rays step in lock-step (same iteration index); a ray that terminates is finalised at once (sky,
-// effects, store) and its half is parked on a harmless far-away state until its partner finishes.
-// =====================================================================================================
-constexpr int kTile2W = 16;
-
-template <bool SPIN, bool MEDIA>
-__global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel2(const __grid_constant__ FrameArgs A) {
-    using rrt::F2;
-    using rrt::V3x2;
-    const Consts& C = A.C;
-    const int lane = threadIdx.x & 31;
-    const int ntx = (A.w + kTile2W - 1) / kTile2W;
-    const int nty = (A.local_rows + kTileH - 1) / kTileH;
-    const unsigned ntiles = (unsigned)(ntx * nty);
-    const rrt::K2 k2 = rrt::make_k2(C);
-    const F2 kHalf = rrt::bc(0.5f);
-    const int max_steps = C.max_steps;
-    const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
-    const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
-    const V3 cam_p = mk(A.cam.pos[0], A.cam.pos[1], A.cam.pos[2]);
-    const bool fast_ok = rrt::dot3(cam_p, cam_p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
-    const V3 park_p = mk(1000.0f, 0.0f, 0.0f), park_v = mk(0.0f, 0.0f, 0.0f);  // inert state of a finished half
-
-    unsigned long long c_steps = 0, c_disk = 0, c_dust = 0, c_dense = 0;
-    unsigned c_cap = 0, c_esc = 0, c_exh = 0, c_touch = 0;
-
-    for (;;) {
-        unsigned tile = 0;
-        if (lane == 0) tile = atomicAdd(A.ticket, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
-        const int tx = (int)(tile % (unsigned)ntx), kk = (int)(tile / (unsigned)ntx);
-        const int cc = nty >> 1, mm = min(cc, nty - 1 - cc);  // centre-out row order, see render_kernel
-        int ty;
-        if (kk <= 2 * mm) ty = (kk & 1) ? cc + ((kk + 1) >> 1) : cc - (kk >> 1);
-        else ty = (cc > nty - 1 - cc) ? (cc - mm - 1) - (kk - (2 * mm + 1)) : (cc + mm + 1) + (kk - (2 * mm + 1));
-        const int x0 = tx * kTile2W + 2 * (lane & 7);
-        const int ly = ty * kTileH + (lane >> 3);
-        int y = 0;
-        bool row_ok = ly < A.local_rows;
-        if (row_ok) {
-            const int grp = ly / A.band_group;
-            y = (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
-            row_ok = y < A.h;
-        }
-        bool alive[2] = {row_ok && x0 < A.w, row_ok && x0 + 1 < A.w};
-        if (!alive[0] && !alive[1]) continue;
-
-        V3x2 P, V;
-        {
-            const V3 vA = alive[0] ? ray_dir(A, x0, y) : park_v, vB = alive[1] ? ray_dir(A, x0 + 1, y) : park_v;
-            const V3 pA = alive[0] ? cam_p : park_p, pB = alive[1] ? cam_p : park_p;
-            P.x = rrt::pk(pA.x, pB.x); P.y = rrt::pk(pA.y, pB.y); P.z = rrt::pk(pA.z, pB.z);
-            V.x = rrt::pk(vA.x, vB.x); V.y = rrt::pk(vA.y, vB.y); V.z = rrt::pk(vA.z, vB.z);
-        }
-        float Ir[2] = {0.f, 0.f}, Ig[2] = {0.f, 0.f}, Ib[2] = {0.f, 0.f}, T[2] = {1.0f, 1.0f};
-        bool touched[2] = {false, false};
-        unsigned n_disk = 0, n_dust = 0, n_dense = 0;
-
-        // retire one half: count it, run the epilogue, park its state
-        auto retire = [&](int hf, int steps, unsigned end, float Tend) {
-            const V3 p = rrt::half_of(P, hf), v = rrt::half_of(V, hf);
-            finish_ray(A, x0 + hf, y, ly, Ir[hf], Ig[hf], Ib[hf], Tend, p, v, steps, end | (touched[hf] ? kEndTouched : 0u));
-            c_steps += (unsigned)steps;
-            c_cap += (end & kEndCaptured) ? 1u : 0u;
-            c_exh += (end & kEndExhausted) ? 1u : 0u;
-            c_esc += (end & (kEndCaptured | kEndExhausted)) ? 0u : 1u;
-            c_touch += touched[hf] ? 1u : 0u;
-            alive[hf] = false;
-            rrt::set_half(P, hf, park_p);
-            rrt::set_half(V, hf, park_v);
-        };
-
-        int it = 0;
-#pragma unroll 1
-        for (; it < max_steps; ++it) {                                                       // :41
-            F2 R2 = rrt::dot2(P, P, k2);
-            F2 R = rrt::sqrt2(R2, k2);                                                       // :44
-            float r[2];
-            rrt::upk(R, r[0], r[1]);
-            bool parked = false;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
-                if (alive[hf] && r[hf] < C.horizon_r) {                                      // :47-51
-                    retire(hf, it, kEndCaptured, 0.0f);
-                    r[hf] = 1000.0f;
-                    parked = true;
-                }
-            if (!(alive[0] || alive[1])) break;
-            if (parked) {  // radius of the parked half only, so the step below stays in the fast domain
-                float r2l, r2h;
-                rrt::upk(R2, r2l, r2h);
-                R = rrt::pk(r[0], r[1]);
-                R2 = rrt::pk(alive[0] ? r2l : 1.0e6f, alive[1] ? r2h : 1.0e6f);
-            }
-            float h[2], h6[2];
-            unsigned zones[2];
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                h[hf] = C.h[0];
-                h6[hf] = C.h6[0];
-                zones[hf] = 0u;
-                if (r[hf] < zone_rmax) {
-                    const float py = rrt::half_of(P.y, hf);
-                    const bool near_bh = r[hf] < 18.0f;                                      // :56
-                    const bool disk_zone = fabsf(py) < C.disk_zone_y && r[hf] < C.disk_zone_r;   // :57
-                    const bool dust_zone = fabsf(py) < C.dust_zone_y && r[hf] < C.dust_zone_r;   // :58
-                    const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));      // :60-62
-                    h[hf] = C.h[zi];
-                    h6[hf] = C.h6[zi];
-                    zones[hf] = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);
-                }
-            }
-            const F2 H = rrt::pk(h[0], h[1]), H6 = rrt::pk(h6[0], h6[1]);
-            const F2 HH = rrt::mul2_raw(H, kHalf);  // exact (power of two)
-            const V3x2 Q = P, Vin = V;          // pre-step state: media and the escape test use Q (:68-69, :120)
-            float rmin[2];
-            rrt::rk4_step2<SPIN>(k2, P, V, H, HH, H6, R2, R, rmin[0], rmin[1]);              // :64
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
-                if (alive[hf] && (!fast_ok || rmin[hf] < C.acc_rmin)) {  // general-domain redo, see render_kernel
-                    const PV s = rk4_step_general<SPIN>(C, rrt::half_of(Q, hf), rrt::half_of(Vin, hf), h[hf], h[hf] * 0.5f, h6[hf]);
-                    rrt::set_half(P, hf, s.p);
-                    rrt::set_half(V, hf, s.v);
-                }
-            if (MEDIA) {
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf)
-                    if (alive[hf] && zones[hf]) {                                            // :67
-                        n_disk += zones[hf] & 1u;
-                        n_dust += zones[hf] >> 1;
-                        const MediaOut m = media_sample(C, rrt::half_of(Q, hf), rrt::half_of(V, hf), r[hf], h[hf], A.time, zones[hf]);
-                        if (m.dense) {                                                       // :71
-                            touched[hf] = true;
-                            ++n_dense;
-                            const float wgt = (1.0f - m.s) * T[hf];                          // :109
-                            Ir[hf] += m.er * wgt; Ig[hf] += m.eg * wgt; Ib[hf] += m.eb * wgt;    // :111-113
-                            T[hf] *= m.s;                                                    // :115
-                        }
-                    }
-            }
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf)
-                if (alive[hf] && r[hf] > 250.0f && rrt::dot3(rrt::half_of(Q, hf), rrt::half_of(V, hf)) > 0.0f)   // :120
-                    retire(hf, it + 1, 0u, T[hf]);
-        }
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf)
-            if (alive[hf]) retire(hf, it, kEndExhausted, T[hf]);  // the loop ran out (:41)
-        c_disk += n_disk; c_dust += n_dust; c_dense += n_dense;
-    }
-
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        c_steps += __shfl_xor_sync(0xffffffffu, c_steps, o);
-        c_disk += __shfl_xor_sync(0xffffffffu, c_disk, o);
-        c_dust += __shfl_xor_sync(0xffffffffu, c_dust, o);
-        c_dense += __shfl_xor_sync(0xffffffffu, c_dense, o);
-        c_cap += __shfl_xor_sync(0xffffffffu, c_cap, o);
-        c_esc += __shfl_xor_sync(0xffffffffu, c_esc, o);
-        c_exh += __shfl_xor_sync(0xffffffffu, c_exh, o);
-        c_touch += __shfl_xor_sync(0xffffffffu, c_touch, o);
-    }
-    if (lane == 0 && A.counters) {
-        atomicAdd(A.counters + 0, c_steps);
-        atomicAdd(A.counters + 1, c_disk);
-        atomicAdd(A.counters + 2, c_dust);
-        atomicAdd(A.counters + 3, c_dense);
-        atomicAdd(A.counters + 4, (unsigned long long)c_cap);
-        atomicAdd(A.counters + 5, (unsigned long long)c_esc);
-        atomicAdd(A.counters + 6, (unsigned long long)c_exh);
-        atomicAdd(A.counters + 7, (unsigned long long)c_touch);
-    }
-}
-
-// =====================================================================================================
-// render_kernel3 (opt-in, RRT_KERNEL_VARIANT=3; bit-identical output, slower than render_kernel at N=1 -- see
-// profiles/r1_history.md "wavefront-in-a-warp experiment"): a wavefront inside every persistent warp.
-//
-// What limits render_kernel on B200 is not the vacuum step (straight-line FMA code, all lanes busy) but the
-// side work: media samples evaluated under per-lane branches, and the fact that one 8x4 tile of disk-plane
-// rays is ~5e6 warp-instructions of sequential work, which is what a band-parallel 8-GPU frame ends up
-// waiting for.  Here:
-//   * every lane owns one ray and is refilled individually from a global ticket when its ray ends
-//     (persistent threads with lane refill).  Tickets are 4-pixel strips and 8 consecutive strips come from
-//     8 distant parts of the centre-out ordered frame, so the expensive disk-plane rays are spread four to
-//     a warp instead of 32 to a warp;
-//   * a lane that is inside a medium does not evaluate it: it appends a SAMPLE JOB (pre-step position,
-//     post-step velocity, zone bits, step-size index, owner lane) to a per-warp ring in shared memory and
-//     keeps stepping.  Every kBurst iterations the warp pumps the ring through three stages, each run with
-//     one job per lane as soon as 32 jobs are waiting for it:
-//        1. disk density + dust envelope of 32 consecutive jobs (survivors of the envelope test are listed),
-//        2. the domain-warped ridge noise of 32 listed dust jobs,
-//        3. redshift / emission / exp(-tau) of 32 consecutive completed jobs, after which every owner lane
-//           folds the results of ITS jobs into its (I, T) registers in ring order.
-//     The ring is FIFO and a ray's jobs are appended in step order, so each ray sees exactly the
-//     reference's sequence of I += e(1-s)T; T *= s updates (raymarcher.cu:107-115): results are
-//     bit-identical to render_kernel;
-//   * a ray that ends with jobs still in the ring forces a drain first; the capture rule T = 0
-//     (raymarcher.cu:49) is applied when the ray is finalised, after its queued emission has been added with
-//     the running T.
-// =====================================================================================================
-constexpr int kStripW = 4;       // pixels per ticket strip
-constexpr int kInterleave = 8;   // consecutive strips are taken from this many distant parts of the frame
-constexpr int kRing = 256;       // sample-job slots per warp (power of two)
-constexpr int kBurst = 2;        // loop iterations between two control points
-constexpr int kRetireMin = 4;    // finished lanes wait until this many can be finalised + refilled together
-
-struct WarpQueue {
-    float qx[kRing], qy[kRing], qz[kRing], vx[kRing], vy[kRing], vz[kRing];
-    float dd[kRing], dc[kRing];   // densities, filled by stages 1 and 2 (dc holds the dust envelope in between)
-    unsigned meta[kRing];         // owner lane | zones << 5 | step-size index << 7
-    unsigned dlist[kRing];        // ring of job sequence numbers waiting for stage 2
-    float er[32], eg[32], eb[32], s[32];  // stage-3 results of the batch being folded
-    unsigned tail;                // sequence number of the next job
-};
-
-// ticket -> pixel.  Tickets count pixels of 4x1 strips; strip s is strip (s % 8) * part + s / 8 of the base order,
-// the base order being rows from the band centre outwards (see render_kernel), left to right.
-__device__ __forceinline__ bool ticket_pixel(const FrameArgs& A, unsigned idx, int spr, unsigned nstrips, unsigned part, int& x,
-                                             int& ly) {
-    const unsigned s = idx / kStripW, l = idx - s * kStripW;
-    const unsigned j = s % kInterleave, b = j * part + s / kInterleave;
-    if (b >= nstrips) return false;
-    const int k = (int)(b / (unsigned)spr), sx = (int)(b - (unsigned)k * (unsigned)spr);
-    const int rows = A.local_rows, c = rows >> 1, m = min(c, rows - 1 - c);
-    if (k <= 2 * m) ly = (k & 1) ? c + ((k + 1) >> 1) : c - (k >> 1);
-    else ly = (c > rows - 1 - c) ? (c - m - 1) - (k - (2 * m + 1)) : (c + m + 1) + (k - (2 * m + 1));
-    x = sx * kStripW + (int)l;
-    return x < A.w;
-}
-__device__ __forceinline__ int band_row(const FrameArgs& A, int ly) {
-    const int grp = ly / A.band_group;
-    return (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
-}
-
-template <bool SPIN, bool MEDIA>
-__global__ void __launch_bounds__(kBlock, RRT_MIN_BLOCKS) render_kernel3(const __grid_constant__ FrameArgs A) {
-    __shared__ WarpQueue s_queue[MEDIA ? kBlock / 32 : 1];
-    WarpQueue& Q = s_queue[MEDIA ? (threadIdx.x >> 5) : 0];
-    const Consts& C = A.C;
-    const unsigned FULL = 0xffffffffu, RM = kRing - 1;
-    const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
-    const int spr = (A.w + kStripW - 1) / kStripW;
-    const unsigned nstrips = (unsigned)spr * (unsigned)A.local_rows;
-    const unsigned part = (nstrips + kInterleave - 1) / kInterleave;
-    const unsigned total = part * kInterleave * kStripW;
-    const int max_steps = C.max_steps;
-    const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
-    const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
-    const V3 cam_p = mk(A.cam.pos[0], A.cam.pos[1], A.cam.pos[2]);
-    const bool fast_ok = rrt::dot3(cam_p, cam_p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
-
-    unsigned long long c_steps = 0;
-    unsigned c_disk = 0, c_dust = 0, c_dense = 0, c_cap = 0, c_esc = 0, c_exh = 0, c_touch = 0;
-
-    enum : int { kEmpty = 0, kActive = 1, kDone = 2 };
-    int st = kEmpty;
-    unsigned end = 0;      // kEnd* bits of the current ray
-    unsigned npend = 0;    // this lane's jobs not yet folded
-    V3 p = cam_p, v = mk(0.f, 0.f, 0.f);
-    float Ir = 0.f, Ig = 0.f, Ib = 0.f, T = 1.0f;
-    int it = 0, x = 0, ly = 0;
-    // warp-uniform ring state (sequence numbers; slot = seq & RM):  head <= s1 <= tail
-    unsigned head = 0;     // oldest job not yet folded
-    unsigned s1 = 0;       // next job for stage 1
-    unsigned dhead = 0, dtail = 0;  // stage-2 list
-    unsigned wit = 0;      // control points seen
-    bool tickets_left = true;
-    if (MEDIA) {
-        if (lane == 0) Q.tail = 0u;
-        __syncwarp();
-    }
-
-    // Run every stage that has a full batch; with drain = true run them until the ring is empty.
-    auto pump = [&](bool drain) {
-        __syncwarp();
-        const unsigned tail = *(volatile unsigned*)&Q.tail;
-        // ---- stage 1: disk density (:68) and dust envelope (densities.h:70-84) ----
-        while (tail - s1 >= 32u || (drain && tail != s1)) {
-            const unsigned n = min(32u, tail - s1);
-            bool need = false;
-            unsigned seq = s1 + lane;
-            if (lane < n) {
-                const unsigned sl = seq & RM, m = Q.meta[sl];
-                const V3 jq = mk(Q.qx[sl], Q.qy[sl], Q.qz[sl]);
-                Q.dd[sl] = (m & 32u) ? rrt::disk_density(C, jq, A.time) : 0.0f;
-                const float base = (m & 64u) ? rrt::dust_base(C, jq) : 0.0f;
-                Q.dc[sl] = base;
-                need = base != 0.0f;
-            }
-            const unsigned nm = __ballot_sync(FULL, need);
-            if (need) Q.dlist[(dtail + (unsigned)__popc(nm & lt_mask)) & RM] = seq;
-            dtail += (unsigned)__popc(nm);
-            s1 += n;
-            __syncwarp();
-        }
-        // ---- stage 2: dust strands (densities.h:86-131) ----
-        while (dtail - dhead >= 32u || (drain && dtail != dhead)) {
-            const unsigned n = min(32u, dtail - dhead);
-            if (lane < n) {
-                const unsigned sl = Q.dlist[(dhead + lane) & RM] & RM;
-                const V3 jq = mk(Q.qx[sl], Q.qy[sl], Q.qz[sl]);
-                Q.dc[sl] = rrt::dust_strands(C, jq, A.time, Q.dc[sl]);                        // :69
-            }
-            dhead += n;
-            __syncwarp();
-        }
-        // ---- stage 3: transfer of completed jobs, in ring order ----
-        const unsigned ready = (dhead == dtail) ? s1 : Q.dlist[dhead & RM];  // first job still waiting for stage 2
-        while (ready - head >= 32u || (drain && ready != head)) {
-            const unsigned n = min(32u, ready - head);
-            const bool have = lane < n;
-            unsigned owner = 0;
-            bool dense = false;
-            if (have) {
-                const unsigned sl = (head + lane) & RM, m = Q.meta[sl];
-                owner = m & 31u;
-                const V3 jq = mk(Q.qx[sl], Q.qy[sl], Q.qz[sl]);
-                const V3 jv = mk(Q.vx[sl], Q.vy[sl], Q.vz[sl]);
-                const float jr = rrt::sqrt_rn_fast(rrt::dot3(jq, jq));  // the loop header's r of that step (:43-44)
-                const unsigned zi = m >> 7;
-                const float jh = zi == 1u ? C.h[1] : (zi == 2u ? C.h[2] : (zi == 3u ? C.h[3] : C.h[0]));
-                const MediaOut o = media_final(C, jq, jv, jr, jh, Q.dd[sl], Q.dc[sl]);
-                dense = o.dense != 0;
-                Q.er[lane] = o.er; Q.eg[lane] = o.eg; Q.eb[lane] = o.eb; Q.s[lane] = o.s;
-            }
-            const unsigned dense_m = __ballot_sync(FULL, dense);
-            unsigned mine = n >= 32u ? FULL : ((1u << n) - 1u);  // becomes: batch entries owned by this lane
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const unsigned bk = __ballot_sync(FULL, have && ((owner >> k) & 1u));
-                mine &= ((lane >> k) & 1u) ? bk : ~bk;
-            }
-            __syncwarp();
-            npend -= (unsigned)__popc(mine);
-            mine &= dense_m;                                                                  // :71
-            while (mine) {
-                const int j = __ffs((int)mine) - 1;
-                mine &= mine - 1u;
-                const float s = Q.s[j];
-                const float wgt = (1.0f - s) * T;                                             // :109
-                Ir += Q.er[j] * wgt; Ig += Q.eg[j] * wgt; Ib += Q.eb[j] * wgt;                // :111-113
-                T *= s;                                                                       // :115
-                end |= kEndTouched;
-                ++c_dense;
-            }
-            head += n;
-            __syncwarp();
-        }
-    };
-
-    for (;;) {
-        // ---- control point: finalise finished rays, refill empty lanes ----
-        const unsigned act_m = __ballot_sync(FULL, st == kActive);
-        const unsigned done_m = __ballot_sync(FULL, st == kDone);
-        if (act_m == 0u || (done_m != 0u && (__popc(done_m) >= kRetireMin || (wit & 15u) == 0u))) {
-            if (done_m) {
-                if (MEDIA && __any_sync(FULL, st == kDone && npend != 0u)) pump(true);
-                if (st == kDone) {                                                            // reference :123-173
-                    const bool captured = (end & kEndCaptured) != 0;
-                    finish_ray(A, x, band_row(A, ly), ly, Ir, Ig, Ib, captured ? 0.0f : T, p, v, it, end);   // T = 0: :49
-                    c_steps += (unsigned)it;
-                    c_cap += captured ? 1u : 0u;
-                    c_exh += (end & kEndExhausted) ? 1u : 0u;
-                    c_esc += (end & (kEndCaptured | kEndExhausted)) ? 0u : 1u;
-                    c_touch += (end & kEndTouched) ? 1u : 0u;
-                    st = kEmpty;
-                }
-            }
-            if (tickets_left) {
-                const unsigned empty_m = __ballot_sync(FULL, st == kEmpty);
-                const unsigned n = (unsigned)__popc(empty_m);
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(A.ticket, n);
-                base = __shfl_sync(FULL, base, 0);
-                if (base + n >= total) tickets_left = false;
-                if (st == kEmpty) {
-                    const unsigned idx = base + (unsigned)__popc(empty_m & lt_mask);
-                    if (idx < total && ticket_pixel(A, idx, spr, nstrips, part, x, ly)) {
-                        p = cam_p;
-                        v = ray_dir(A, x, band_row(A, ly));                                   // :20-34
-                        Ir = 0.f; Ig = 0.f; Ib = 0.f; T = 1.0f;                               // :36-38
-                        it = 0;
-                        end = max_steps > 0 ? 0u : kEndExhausted;
-                        st = max_steps > 0 ? kActive : kDone;
-                    }
-                }
-            }
-            if (!__any_sync(FULL, st != kEmpty)) {
-                if (!tickets_left) break;
-                continue;
-            }
-        }
-        ++wit;
-
-        // ---- kBurst loop iterations of reference :41-121 for every active lane, no warp-wide operation inside ----
-#pragma unroll 1
-        for (int b = 0; b < kBurst; ++b) {
-            if (st == kActive) {
-                const float r2 = rrt::dot3(p, p);
-                const float r = rrt::sqrt_rn_fast(r2);                                        // :44
-                if (r < C.horizon_r) {                                                        // :47-51
-                    st = kDone;
-                    end |= kEndCaptured;
-                } else {
-                    bool disk_zone = false, dust_zone = false;
-                    int zi = 0;
-                    float h = C.h[0], h6 = C.h6[0];
-                    if (r < zone_rmax) {
-                        const bool near_bh = r < 18.0f;                                       // :56
-                        disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;          // :57
-                        dust_zone = fabsf(p.y) < C.dust_zone_y && r < C.dust_zone_r;          // :58
-                        zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));             // :60-62
-                        // selects between uniform constants, not an indexed constant load: lanes of one warp are in
-                        // different zones here and a divergent c[][] index is replayed per distinct address
-                        h = near_bh ? C.h[1] : (disk_zone ? C.h[2] : (dust_zone ? C.h[3] : C.h[0]));
-                        h6 = near_bh ? C.h6[1] : (disk_zone ? C.h6[2] : (dust_zone ? C.h6[3] : C.h6[0]));
-                    }
-                    const float hh = h * 0.5f;  // exact
-                    const V3 q = p, v_in = v;
-                    const float rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);   // :64
-                    if (!fast_ok || rmin < C.acc_rmin) {  // general-domain redo, see render_kernel
-                        const PV sres = rk4_step_general<SPIN>(C, q, v_in, h, hh, h6);
-                        p = sres.p; v = sres.v;
-                    }
-                    ++it;
-                    if (MEDIA && (disk_zone || dust_zone)) {                                  // :67
-                        const unsigned zones = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);
-                        c_disk += zones & 1u;
-                        c_dust += zones >> 1;
-                        if (zones) {
-                            // both density functions return 0 outside ISCO <= R <= DISK_OUT (densities.h:21-23,
-                            // 70-72): only samples inside that ring become jobs
-                            const float R = rrt::sqrt_rn_fast(q.x * q.x + 0.0f * 0.0f + q.z * q.z);
-                            if (R >= C.isco && R <= C.disk_out) {
-                                // warp-aggregated append: one shared-memory atomic per converged group of lanes
-                                const unsigned am = __activemask();
-                                const int leader = __ffs((int)am) - 1;
-                                unsigned seq = 0;
-                                if ((int)lane == leader) seq = atomicAdd(&Q.tail, (unsigned)__popc(am));
-                                seq = __shfl_sync(am, seq, leader) + (unsigned)__popc(am & lt_mask);
-                                const unsigned sl = seq & RM;
-                                Q.qx[sl] = q.x; Q.qy[sl] = q.y; Q.qz[sl] = q.z;
-                                Q.vx[sl] = v.x; Q.vy[sl] = v.y; Q.vz[sl] = v.z;               // post-step velocity (:77)
-                                Q.meta[sl] = lane | (zones << 5) | ((unsigned)zi << 7);
-                                ++npend;
-                            }
-                        }
-                    }
-                    if (r > 250.0f && rrt::dot3(q, v) > 0.0f) st = kDone;                     // :120
-                    else if (it >= max_steps) { st = kDone; end |= kEndExhausted; }           // :41
-                }
-            }
-        }
-        if (MEDIA) {
-            __syncwarp();
-            const unsigned tail = *(volatile unsigned*)&Q.tail;
-            if (tail - s1 >= 32u) pump(false);
-            if (tail - head > (unsigned)(kRing - 32 * kBurst)) pump(true);  // no room for another burst: drain
-        }
-    }
-
-    // one set of atomics per warp
-    unsigned long long w_disk = c_disk, w_dust = c_dust, w_dense = c_dense;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        c_steps += __shfl_xor_sync(FULL, c_steps, o);
-        w_disk += __shfl_xor_sync(FULL, w_disk, o);
-        w_dust += __shfl_xor_sync(FULL, w_dust, o);
-        w_dense += __shfl_xor_sync(FULL, w_dense, o);
-        c_cap += __shfl_xor_sync(FULL, c_cap, o);
-        c_esc += __shfl_xor_sync(FULL, c_esc, o);
-        c_exh += __shfl_xor_sync(FULL, c_exh, o);
-        c_touch += __shfl_xor_sync(FULL, c_touch, o);
-    }
-    if (lane == 0 && A.counters) {
-        atomicAdd(A.counters + 0, c_steps);
-        atomicAdd(A.counters + 1, w_disk);
-        atomicAdd(A.counters + 2, w_dust);
-        atomicAdd(A.counters + 3, w_dense);
-        atomicAdd(A.counters + 4, (unsigned long long)c_cap);
-        atomicAdd(A.counters + 5, (unsigned long long)c_esc);
-        atomicAdd(A.counters + 6, (unsigned long long)c_exh);
-        atomicAdd(A.counters + 7, (unsigned long long)c_touch);
-    }
-}
 
 // ---- band assembly on the encoding GPU ------------------------------------------------------------
 __global__ void assemble_kernel(const uchar4* __restrict__ packed, int rows_per_rank, int w, int h, int nranks,
