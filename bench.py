@@ -50,7 +50,10 @@ def parse():
     ap.add_argument("--strict", action="store_true",
                     help="experiment only: clear RRT_FLAG_FMAD (unfused arithmetic, the twin of the reference headers on a host) "
                          "instead of the default contract, the arithmetic of the reference's own CUDA build")
-    ap.add_argument("--depth", type=int, default=2, help="frames in flight in the timed sequence (1 = one at a time)")
+    ap.add_argument("--depth", type=int, default=0,
+                    help="frames in flight in the timed sequence (1..4); 0 (default) = pick the schedule at start-up")
+    ap.add_argument("--share", type=int, default=-1,
+                    help="with --depth: rrt_set_frames_in_flight value, each launch gets 1/share of the CTA slots (default 1)")
     ap.add_argument("--workload", default="frame", choices=["frame", "path"],
                     help="frame (default, the headline: one 4K frame cut into row bands) or path (BASELINE config 5: "
                          "the 300-frame 'Gargantua Fly-By' at 1080p, frame k on GPU k mod N, sustained frames/s)")
@@ -173,7 +176,7 @@ def run_path_workload(args, r, sky, prm, world, rank, dev):
     from relativisticraytracer_b200.parallel import PathSequence
     w, h = (1920, 1080) if (args.width, args.height) == (W4K, H4K) else (args.width, args.height)
     fx = rrt.default_effects()
-    seq = PathSequence(r, w, h, depth=max(1, min(args.depth, 4)))
+    seq = PathSequence(r, w, h, depth=max(1, min(args.depth, 4)) if args.depth > 0 else 2)
     n = args.path_frames
 
     def barrier():
@@ -313,14 +316,13 @@ def main():
         return total_ms, kernel_ms, launches
 
     from relativisticraytracer_b200.parallel import FramePipeline
-    depth = max(1, min(args.depth, 4))
-    pipe_dev = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=False)
-    pipe_host = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=True)
 
-    def timed_sequence(pipe, n_steps: int):
-        """K frames as a sequence with `depth` frames in flight (frame k on stream k % depth), the whole
-        sequence bracketed by barrier + synchronize.  Returns (device ms by CUDA events, host wall ms, launches)."""
+    def timed_sequence(pipe, share: int, n_steps: int):
+        """K frames as a sequence with pipe.depth frames in flight (frame k on stream k % depth), each launch on
+        1/share of the resident-CTA slots, the whole sequence bracketed by barrier + synchronize.
+        Returns (device ms by CUDA events, host wall ms, launches)."""
         launches = 0
+        r.set_frames_in_flight(share)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -335,11 +337,38 @@ def main():
         torch.cuda.synchronize()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
+        r.set_frames_in_flight(1)
         return e0.elapsed_time(e1), wall_ms, launches
+
+    # How the sequence is scheduled.  A frame's kernel cannot finish faster than its critical path (one tile of
+    # disk-plane rays, ~17 ms at 4K); when that is long against the frame's share of the work (band-parallel frames
+    # at N >= 4) more frames in flight on a share of the CTA slots each keep the SMs busy, otherwise two frames
+    # in flight on the whole GPU are best.  Unless --depth/--share pin it, both schedules are tried on a short
+    # sequence at start-up and the faster one is used (the same on every rank: max over ranks decides).
+    if args.depth > 0:
+        depth = max(1, min(args.depth, 4))
+        share = args.share if args.share > 0 else 1
+        schedule_how = "fixed by --depth/--share"
+    else:
+        cands = [(2, 1), (4, 2)]
+        trial = []
+        for d_, s_ in cands:
+            pp = FramePipeline(r, w, h, BAND_GROUP, depth=d_, to_host=False)
+            timed_sequence(pp, s_, d_)                                     # warm the streams / buffers
+            ms, _, _ = timed_sequence(pp, s_, 8)
+            tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            trial.append(float(tm.item()) / 8)
+            del pp
+        depth, share = cands[min(range(len(cands)), key=lambda i: trial[i])]
+        schedule_how = "auto: " + ", ".join(f"depth {d_} on 1/{s_} of the CTA slots = {t_:.2f} ms/frame" for (d_, s_), t_ in zip(cands, trial))
+    pipe_dev = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=False)
+    pipe_host = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=True)
 
     # ---- warm-up, then the counted work of one step -------------------------------------------------
     timed(args.warmup, False)
-    timed_sequence(pipe_dev, min(args.warmup, depth))
+    timed_sequence(pipe_dev, share, min(max(args.warmup, 1), depth))
     r.read_counters(reset=True)
     one_frame(False)
     torch.cuda.synchronize()
@@ -353,10 +382,10 @@ def main():
     lat_ms, kern_ms, _ = timed(args.steps, False)
     # ---- timed region: K frames, device-resident, `depth` in flight -------------------------------------
     with ClockSampler(dev) as clk:
-        tot_ms, _, launches = timed_sequence(pipe_dev, args.steps)
+        tot_ms, _, launches = timed_sequence(pipe_dev, share, args.steps)
     # ---- timed region: end to end (HOST destination, device->host copy inside) --------------------------
-    timed_sequence(pipe_host, min(2, args.steps))
-    _, e2e_ms, _ = timed_sequence(pipe_host, args.steps)
+    timed_sequence(pipe_host, share, min(2, args.steps))
+    _, e2e_ms, _ = timed_sequence(pipe_host, share, args.steps)
 
     t = torch.tensor([tot_ms, kern_ms, e2e_ms, lat_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -396,7 +425,7 @@ def main():
         "config": {"workload": WORKLOAD if (w, h, args.flags, args.camera) == (W4K, H4K, 3, "C0") else f"EXPERIMENT {w}x{h} flags={args.flags} camera={args.camera} variant of: {WORKLOAD}",
                    "width": w, "height": h, "spin_a": SPIN, "media": "disk+dust", "camera": "C0", "band_group_rows": BAND_GROUP,
                    "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) before every frame",
-                   "frames_in_flight": depth,
+                   "frames_in_flight": depth, "cta_slots_per_frame": f"1/{share}", "schedule": schedule_how,
                    "rounding_contract": ("strict: unfused mul+add, the twin of the reference headers on a host" if args.strict else
                                          "fmad: the FMA fusion schedule of the reference's own CUDA build (default)"),
                    "rk4_steps_per_frame": rk4_per_frame, "disk_evals_per_frame": disk_evals, "dust_evals_per_frame": dust_evals},

@@ -161,6 +161,11 @@ int rrt_render_host(rrt_context* ctx, const rrt_params* prm, const rrt_camera* c
 int rrt_render_host_async(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx,
                           uint64_t sky_texture, float time, int w, int h, uint8_t* host_rgba, int slot, void* stream);
 
+/* How many rrt_render launches the caller keeps running concurrently on different streams (1 .. RRT_HOST_SLOTS,
+ * default 1).  Each launch then occupies 1/n of the GPU's resident-CTA slots, so the n frames share the SMs from
+ * the start instead of each filling the GPU and ending in a drain; results do not depend on it. */
+int rrt_set_frames_in_flight(rrt_context* ctx, int n);
+
 /* Number of rows a band owns in an h-row image (packed buffer height). */
 int rrt_band_rows(const rrt_band* band, int h);
 

@@ -75,7 +75,7 @@ SYMBOLS = [
     "rrt_disk_density_batch", "rrt_dust_density_batch", "rrt_sky_sample_batch", "rrt_fp32_peak_probe",
     "rrt_camera_from", "rrt_path_count", "rrt_path_name", "rrt_path_num_keys", "rrt_path_duration",
     "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest",
-    "rrt_set_probe_contract", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
+    "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load() -> C.CDLL:
     lib.rrt_path_clock.argtypes = [ci, cf]
     lib.rrt_path_clock.restype = cf
     lib.rrt_set_probe_contract.argtypes = [vp, ci]
+    lib.rrt_set_frames_in_flight.argtypes = [vp, ci]
     lib.rrt_sink_open.argtypes = [C.c_char_p, ci, ci, ci, ci, P(vp)]
     lib.rrt_sink_write.argtypes = [vp, vp]
     lib.rrt_sink_frames.argtypes = [vp]

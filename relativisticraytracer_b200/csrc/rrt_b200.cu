@@ -102,6 +102,7 @@ struct rrt_context {
     void* d_frame[RRT_HOST_SLOTS] = {};  // device frames behind the host-destination calls, one per slot
     size_t d_frame_bytes[RRT_HOST_SLOTS] = {};
     bool probe_fmad = false;  // contract of the parameter-less probes (hash31 / noise3D / fbm)
+    int frames_in_flight = 1; // render launches expected to run concurrently: each gets 1/n of the resident-CTA slots
     std::string err;
     std::mutex mu;
 };
@@ -403,7 +404,11 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
     if (per_sm < 1) per_sm = 1;
     const long long rays_per_block = (variant == 2 ? 2 : 1) * (long long)kBlock;
-    long long grid = (long long)ctx->sm_count * per_sm;
+    // A persistent launch normally fills every resident-CTA slot.  When the caller keeps n frames in flight, each
+    // launch takes 1/n of the slots so that the n kernels run side by side from the start: a launch then lasts
+    // n times longer than its critical path (one tile of disk-plane rays, ~17 ms at 4K) needs, instead of ending
+    // in a drain with most SMs idle (rrt_set_frames_in_flight).
+    long long grid = ((long long)ctx->sm_count * per_sm + ctx->frames_in_flight - 1) / ctx->frames_in_flight;
     const long long need = ((long long)w * local_rows + rays_per_block - 1) / rays_per_block;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, kBlock, 0, st>>>(A);
@@ -573,6 +578,13 @@ int rrt_sky_sample_batch(rrt_context* ctx, uint64_t sky_texture, int n, const fl
     int rc = run_probe(ctx, n, k_sky, (cudaTextureObject_t)sky_texture, n, (const float*)dx.p, (const float*)dy.p, (float4*)dout.p);
     if (rc) return rc;
     RRT_CU(ctx, cudaMemcpy(out4, dout.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+int rrt_set_frames_in_flight(rrt_context* ctx, int n) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (n < 1 || n > RRT_HOST_SLOTS) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_set_frames_in_flight: n out of range");
+    ctx->frames_in_flight = n;
     return RRT_OK;
 }
 

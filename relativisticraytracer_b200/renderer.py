@@ -198,6 +198,10 @@ class Renderer:
         self._check(self._lib.rrt_fp32_peak_probe(self._ctx, int(iters), C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
+    def set_frames_in_flight(self, n: int) -> None:
+        """rrt_set_frames_in_flight: each launch takes 1/n of the resident-CTA slots (n concurrent frames)."""
+        self._check(self._lib.rrt_set_frames_in_flight(self._ctx, int(n)))
+
     def set_probe_contract(self, fmad: bool) -> None:
         """Rounding contract of hash31 / noise3d / fbm (the probes without a parameter block)."""
         self._check(self._lib.rrt_set_probe_contract(self._ctx, 1 if fmad else 0))

@@ -4,7 +4,7 @@ tag=$1; n=$2; shift 2
 if [ "$n" = 1 ]; then
   python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-ref-cuda "$@" > gpurun_out/${tag}_n1.log 2>&1
 else
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 "$@" > gpurun_out/${tag}_n$n.log 2>&1
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps ${STEPS:-10} --warmup 3 "$@" > gpurun_out/${tag}_n$n.log 2>&1
 fi
 tail -1 gpurun_out/${tag}_n$n.log | python -c "
 import json,sys
