@@ -1,14 +1,19 @@
-// rrt_b200.cu -- render kernels, probe kernels and the C ABI (include/rrt.h) of librrt_b200.so.
+// rrt_b200.cu -- host side of librrt_b200.so: context, launch logic and the C ABI of include/rrt.h, plus the
+// strict-contract instantiation of the kernels (this unit is compiled -fmad=false; rrt_fmad.cu holds the other).
 //
 // Replaces, for the hot path only, raymarch_kernel + launch_raymarch (reference src/raymarcher.cu:15-180).
-// Compile for sm_100a with -fmad=false (see the rounding contract in rrt_device.cuh).
 //
-// Kernel organisation (B200: 148 SMs, no tensor-core work on this path -- it is FP32 FMA-pipe bound):
-//   * persistent warps: grid = SMs x resident CTAs; each warp pulls 8x4-pixel tiles from a global
-//     atomic ticket until the frame is exhausted, so SMs never idle behind a slow tile;
-//   * ray state (p, v, I, T, counters) lives in registers for the whole ray -- nothing is staged in HBM;
-//   * camera, effects and every derived constant arrive in the kernel parameter block, i.e. the
-//     constant bank, and are read as free FFMA/FMUL operands;
+// Where things are:
+//   include/rrt_device.cuh   device math: the two rounding contracts, geodesic RHS, RK4, noise, densities
+//   csrc/rrt_kernel.cuh      render_kernel (one 8x4 tile per persistent warp), per-ray helpers, probe kernels
+//   csrc/rrt_variants.cuh    two measured alternatives to render_kernel (RRT_KERNEL_VARIANT=2, 3)
+//   this file                band assembly, self-test / roofline probes, rrt_context, every extern "C" entry point
+//
+// Launch organisation (B200: 148 SMs, no tensor-core work on this path -- it is FP32 FMA-pipe bound):
+//   * persistent warps: grid = SMs x resident CTAs (or 1/n of them with n frames in flight); each warp pulls
+//     8x4-pixel tiles from a global atomic ticket until the frame is exhausted;
+//   * ray state lives in registers for the whole ray; camera, effects and every derived constant arrive in the
+//     kernel parameter block (constant bank) and are read as free FFMA/FMUL operands;
 //   * the skybox is a texture object (wrap-x / clamp-y / linear), 33.5 MB, L2-resident;
 //   * outputs: 4 B/pixel uchar4 (row-flipped like the reference) plus optional float4 parity planes.
 #include <cuda_runtime.h>
