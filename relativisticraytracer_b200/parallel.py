@@ -75,6 +75,22 @@ def path_frames(rank: int, nranks: int, n_frames: int):
     return [k for k in range(1, n_frames + 1) if frame_owner(k, nranks) == rank]
 
 
+def path_rounds(n_frames: int, nranks: int, first_frame: int = 1):
+    """Frame-parallel schedule of ``PathSequence``: round j covers the next ``nranks`` consecutive frames and is the
+    list, indexed by rank, of the frame that rank renders -- frame k belongs to rank ``frame_owner(k)`` = k % N --
+    or ``None`` for a rank left without one in the last round.  Every frame first_frame .. first_frame+n_frames-1
+    appears exactly once; within a round the sink takes them in increasing frame number."""
+    rounds = []
+    for j in range((n_frames + nranks - 1) // nranks):
+        rnd = [None] * nranks
+        for i in range(nranks):
+            if j * nranks + i < n_frames:
+                f = first_frame + j * nranks + i
+                rnd[frame_owner(f, nranks)] = f
+        rounds.append(rnd)
+    return rounds
+
+
 class BandedFrame:
     """Buffers + calls for one banded frame on this rank (see module docstring)."""
 
@@ -185,9 +201,9 @@ class PathSequence:
     """Frame-parallel rendering of a keyframe camera path (BASELINE config 5; reference P + R keys:
     PathController playback under the recorder's fixed 1/fps clock, src/main.cpp:171-220, 505-528).
 
-    Frames are 1-based like the recorder counts them.  Round j covers frames j*N+1 .. j*N+N; rank r renders
-    frame j*N+r+1 whole (``frame_owner``), one NCCL gather per round brings the N frames to rank 0 (the
-    encoding GPU), which copies them to pinned host memory and hands them to the sink in frame order.  Rounds
+    Frames are 1-based like the recorder counts them.  Round j covers frames j*N+1 .. j*N+N; frame k is rendered
+    whole by rank k % N (``frame_owner``, ``path_rounds``), one NCCL gather per round brings the N frames to
+    rank 0 (the encoding GPU), which copies them to pinned host memory and hands them to the sink in frame order.  Rounds
     are pipelined ``depth`` deep on separate streams like ``FramePipeline``.  Camera and clock come from the
     C-ABI host functions (``rrt_path_state`` / ``rrt_path_clock``), so frame k is the same pure function of k
     on every rank count."""
@@ -213,7 +229,8 @@ class PathSequence:
         cur = torch.cuda.current_stream(self.r.device)
         for s in self.streams:
             s.wait_stream(cur)
-        rounds = (n_frames + self.world - 1) // self.world
+        schedule = path_rounds(n_frames, self.world, first_frame)
+        rounds = len(schedule)
         in_flight = [None] * self.depth     # per slot: list of frame numbers it holds
         launches = done = 0
 
@@ -223,17 +240,16 @@ class PathSequence:
                 return
             self.events[k].synchronize()
             if self.rank == 0:
-                for i, f in enumerate(in_flight[k]):
-                    if f is not None:
-                        if sink is not None:
-                            sink.write(self.host[k][i])
-                        done += 1
+                for f, i in sorted((f, i) for i, f in enumerate(in_flight[k]) if f is not None):   # frame order
+                    if sink is not None:
+                        sink.write(self.host[k][i])
+                    done += 1
             in_flight[k] = None
 
         for j in range(rounds):
             k = j % self.depth
             retire(k)
-            frames = [first_frame + j * self.world + r if j * self.world + r < n_frames else None for r in range(self.world)]
+            frames = schedule[j]
             mine = frames[self.rank]
             s = self.streams[k]
             with torch.cuda.stream(s):

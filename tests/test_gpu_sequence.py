@@ -57,6 +57,21 @@ def test_frame_pipeline_equals_one_at_a_time(gpu, sky_small, to_host):
         got.append(f.numpy().copy() if to_host else f.cpu().numpy())
     for k in range(len(times)):
         assert np.array_equal(got[k], want[k]), k
+    # sharing the resident-CTA slots between the frames in flight changes the schedule, not the pixels
+    gpu.set_frames_in_flight(2)
+    try:
+        pipe3 = FramePipeline(gpu, W, H, depth=4, to_host=to_host)
+        pipe3.begin()
+        for t in times:
+            pipe3.submit(prm, cam, fx, sky, t)
+        pipe3.end()
+        torch.cuda.synchronize()
+        f = pipe3.last_frame()
+        assert np.array_equal(f.numpy() if to_host else f.cpu().numpy(), want[-1])
+    finally:
+        gpu.set_frames_in_flight(1)
+    with pytest.raises(rrt.RrtError):
+        gpu.set_frames_in_flight(0)
     # and with nothing waiting in between: only the last two frames are still held by the two slots
     pipe2 = FramePipeline(gpu, W, H, depth=2, to_host=to_host)
     pipe2.begin()

@@ -65,3 +65,21 @@ def test_two_rank_band_gather_and_path_split():
         for p in procs:
             p.join(timeout=60)
         assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_path_rounds_cover_every_frame_once_in_order():
+    """frame-parallel schedule of a camera path (BASELINE config 5): pure host logic"""
+    from relativisticraytracer_b200.parallel import frame_owner, path_frames, path_rounds
+    for n_frames in (1, 7, 8, 9, 300):
+        for nranks in (1, 2, 3, 8):
+            for first in (1, 25):
+                rounds = path_rounds(n_frames, nranks, first)
+                assert all(len(rnd) == nranks for rnd in rounds)
+                flat = [f for rnd in rounds for f in sorted(x for x in rnd if x is not None)]
+                assert flat == list(range(first, first + n_frames))                 # sink order = frame order
+                assert all(f is not None for rnd in rounds[:-1] for f in rnd)     # only the last round may be ragged
+                for r in range(nranks):                                            # frame k -> rank k % N
+                    col = [rnd[r] for rnd in rounds if rnd[r] is not None]
+                    assert all(frame_owner(f, nranks) == r for f in col)
+                    if first == 1:
+                        assert col == path_frames(r, nranks, n_frames)
