@@ -8,7 +8,7 @@
  * Parity pin: tests/test_oracle_vs_ref.py checks every entry point bit-for-bit against
  * oracle/_ref/libref_host.so (the reference's own headers compiled for the host) wherever that
  * library is present, and tests/test_oracle_golden.py checks it against tests/golden/ (npz files), which
- * tools/make_golden.py generated from that same reference build.  The reference ships no tests or
+ * tests/tools/make_golden.py generated from that same reference build.  The reference ships no tests or
  * golden vectors of its own, so those two are the whole pin.
  *
  * Canonical rounding: compile with -ffp-contract=off; every + - * / sqrt below is one IEEE

@@ -1,4 +1,4 @@
-"""Seeded input generators shared by the parity tests and tools/make_golden.py."""
+"""Seeded input generators shared by the parity tests and tests/tools/make_golden.py."""
 import numpy as np
 
 RADII = (0.5, 0.99, 1.0, 1.01, 2.0, 2.02, 2.1, 3.0, 6.0, 10.0, 17.99, 18.0, 25.0, 30.0, 60.0, 250.0, 400.0)

@@ -116,7 +116,7 @@ def test_fmad_bytes_equal_reference_cuda_kernel(gpu, sky_small, cam, spin):
     """Against the reference's own CUDA kernel (unmodified src/raymarcher.cu, nvcc defaults, same GPU): every
     pixel whose ray never touched a medium is byte-identical; of the pixels that did (there the density code is
     left to nvcc's own fusion in both builds, which need not coincide) at most a handful differ, by one count.
-    Measured at 960x540 with the 4096x2048 star-field sky, 8 camera/spin cases (tools/refcuda_census.py):
+    Measured at 960x540 with the 4096x2048 star-field sky, 8 camera/spin cases (tests/tools/refcuda_census.py):
     0 of 3.66 M untouched and 2 of 0.49 M touched pixels differ."""
     import relativisticraytracer_b200 as rrt
     from oracle import RefCuda
@@ -135,7 +135,7 @@ def test_fmad_bytes_equal_reference_cuda_kernel(gpu, sky_small, cam, spin):
 @pytest.mark.parametrize("tag,spin", [("a000", 0.0), ("a099", 0.99)])
 def test_fmad_bytes_equal_committed_reference_cuda_frames(gpu, sky_small, cam, tag, spin):
     """Same check against frames of the reference kernel committed under tests/golden/ (generated on a B200 by
-    tools/make_golden_refcuda.py), so the pin does not depend on the reference tree being present."""
+    tests/tools/make_golden_refcuda.py), so the pin does not depend on the reference tree being present."""
     import os
     path = os.path.join(os.path.dirname(__file__), "golden", "refcuda_frames.npz")
     if not os.path.exists(path):

@@ -1,4 +1,4 @@
-"""The oracle port (oracle/rrt_oracle.c) against the committed golden vectors, which tools/make_golden.py
+"""The oracle port (oracle/rrt_oracle.c) against the committed golden vectors, which tests/tools/make_golden.py
 generated from the reference's own headers (oracle/_ref).  Bit-for-bit: same libm, same operations."""
 import hashlib
 import json
@@ -101,7 +101,7 @@ def test_row_ranges_and_empty(ora, sky_small):
 @pytest.mark.parametrize("tag,spin", [("a000", 0.0), ("a099", 0.99)])
 def test_fmad_twin_against_reference_cuda_frames(ora, sky_small, cam, tag, spin):
     """The CPU twin of the FMAD contract (oracle port with ORA_FLAG_FMAD) against uchar4 frames rendered on a B200
-    by the reference's OWN CUDA kernel (tests/golden/refcuda_frames.npz, tools/make_golden_refcuda.py): every byte
+    by the reference's OWN CUDA kernel (tests/golden/refcuda_frames.npz, tests/tools/make_golden_refcuda.py): every byte
     within one count (what host libm vs libdevice atan2f/asinf/expf and the emulated texture filter leave), on
     well under 1 % of the pixels -- whereas the unfused arithmetic is off by up to tens of counts where rays touch
     the media, because the noise hash amplifies the rounding difference of an unfused dot product."""

@@ -1,5 +1,5 @@
 """Multi-rank check of PathSequence (run under torchrun on N GPUs): the raw stream rank 0 writes equals the frames
-rendered one by one on rank 0.  Usage: python -m torch.distributed.run --nproc-per-node N tools/check_path_multirank.py"""
+rendered one by one on rank 0.  Usage: python -m torch.distributed.run --nproc-per-node N tests/tools/check_path_multirank.py"""
 import os
 import sys
 
@@ -7,7 +7,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import relativisticraytracer_b200 as rrt  # noqa: E402
 from relativisticraytracer_b200.parallel import PathSequence  # noqa: E402

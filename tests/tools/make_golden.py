@@ -1,7 +1,7 @@
 """Generate tests/golden/*.npz from the REFERENCE build (oracle/_ref/libref_host.so = the reference's own
 headers compiled for the host with -ffp-contract=off).  Run in the container that has /root/reference:
 
-    python tools/make_golden.py
+    python tests/tools/make_golden.py
 
 The reference ships no tests or golden vectors; these fixtures are the pin for the oracle port
 (tests/test_oracle_golden.py) and travel to the GPU box, where /root/reference does not exist.
@@ -13,7 +13,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -1,6 +1,6 @@
 """Golden uchar4 frames from the reference's OWN CUDA kernel (oracle/_ref/libref_cuda.so = src/raymarcher.cu,
 unmodified, nvcc -O3 sm_100a with nvcc's default flags), rendered on a B200.  Run on the GPU box:
-    python tools/make_golden_refcuda.py gpurun_out/refcuda_frames.npz
+    python tests/tools/make_golden_refcuda.py gpurun_out/refcuda_frames.npz
 and copy the file to tests/golden/.  Inputs are the ones tests/test_gpu_fmad.py re-creates: sky_small
 (procedural_sky(512, 256, seed=1234, stars=400)), reference default CameraEffects, time 1.0, 160x90."""
 import os
@@ -8,7 +8,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import relativisticraytracer_b200 as rrt  # noqa: E402

@@ -1,6 +1,6 @@
 """Byte-level census of our uchar4 frames against the reference's own CUDA kernel (oracle/_ref/libref_cuda.so,
 unmodified src/raymarcher.cu built with nvcc defaults) on the same GPU, for both rounding contracts.
-Usage: python tools/refcuda_census.py [w h]   (GPU box only; test infrastructure)"""
+Usage: python tests/tools/refcuda_census.py [w h]   (GPU box only; test infrastructure)"""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import relativisticraytracer_b200 as rrt  # noqa: E402
