@@ -270,7 +270,8 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
     for (;;) {
         int ev = kRanOut;
         V3 q = p, v_in = v;   // pre-step state: media and the escape test use q (:68-69, :120)
-        float r = 0.0f, h = C.h[0], hh = C.hh[0], h6 = C.h6[0];
+        float r = 0.0f;
+        int zone_index = 0;   // which step size the step used (config.h:47 x {1, 0.1, 0.3, 0.5}); h itself stays in the loop
         unsigned zones = 0;
         // The loop is rotated: |p| of the NEXT iteration's header (:43-44) is computed right after the step, so
         // its multiply -> rsqrt -> refine chain overlaps the escape test and the loop bookkeeping instead of
@@ -285,7 +286,8 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             q = p;
             v_in = v;
             if (!RRT_FMAD || r < zone_rmax) {
-                h = C.h[0]; h6 = C.h6[0];
+                float h = C.h[0], h6 = C.h6[0];
+                int zsel = 0;
                 if (r < zone_rmax) {  // one compare for the steps outside every zone
                     const bool near_bh = r < 18.0f;                                           // :56
                     const bool disk_zone = fabsf(p.y) < C.disk_zone_y && r < C.disk_zone_r;   // :57
@@ -293,17 +295,18 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
                     const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));       // :60-62
                     h = C.h[zi];
                     h6 = C.h6[zi];
+                    zsel = zi;
                     if (MEDIA) z = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);   // :67
                 }
-                hh = h * 0.5f;  // exact
-                rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, hh, h6, r2, r);                   // :64
+                zone_index = zsel;
+                rmin = rrt::rk4_step_fast<SPIN>(C, p, v, h, h * 0.5f /* exact */, h6, r2, r);  // :64
             } else {
                 // FMAD contract only.  3/4 of all steps are outside every zone; their step size is the same for the
                 // whole warp, so this second copy of the step takes h, h/2 and h/6 as constant-bank operands and 24 of
                 // its FFMAs read two registers instead of three.  The fused loop is bound by register-file operand
                 // bandwidth: 4K C0 75.8 -> 74.1 ms.  The strict loop is issue bound and loses 3 % to the
                 // larger code, so it keeps the single copy.
-                h = C.h[0]; hh = C.hh[0]; h6 = C.h6[0];
+                zone_index = 0;
                 rmin = rrt::rk4_step_fast<SPIN>(C, p, v, C.h[0], C.hh[0], C.h6[0], r2, r);    // :64
             }
             zones = z;
@@ -314,7 +317,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             if (MEDIA && z) {
                 n_disk += z & 1u;
                 n_dust += z >> 1;
-                fold(media_sample(C, q, v, r, h, A.time, z));
+                fold(media_sample(C, q, v, r, C.h[zone_index], A.time, z));
             }
             if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { ev = kEscaped; break; }               // :120
             r2 = r2_next;
@@ -322,7 +325,8 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
         }
         if (ev == kRedo) {
             // outside the branch-free domain, or geodesics.h:33 can fire: redo this step with the general code
-            const PV s = rk4_step_general<SPIN>(C, q, v_in, h, hh, h6);
+            const float h = C.h[zone_index];
+            const PV s = rk4_step_general<SPIN>(C, q, v_in, h, h * 0.5f, C.h6[zone_index]);
             p = s.p; v = s.v;
             ++it;
             if (MEDIA && zones) {
