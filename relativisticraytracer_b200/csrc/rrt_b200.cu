@@ -406,9 +406,10 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     // the job rings of render_kernel3 want the large shared-memory carve-out (43 KB per CTA, 5 CTAs per SM)
     RRT_CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
-    RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, 0));
+    const int block = variant == 1 ? kRenderBlock : kBlock;
+    RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0));
     if (per_sm < 1) per_sm = 1;
-    const long long rays_per_block = (variant == 2 ? 2 : 1) * (long long)kBlock;
+    const long long rays_per_block = (variant == 2 ? 2 : 1) * (long long)block;
     // A persistent launch normally fills every resident-CTA slot.  When the caller keeps n frames in flight, each
     // launch takes 1/n of the slots so that the n kernels run side by side from the start: a launch then lasts
     // n times longer than its critical path (one tile of disk-plane rays, ~17 ms at 4K) needs, instead of ending
@@ -416,7 +417,7 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     long long grid = ((long long)ctx->sm_count * per_sm + ctx->frames_in_flight - 1) / ctx->frames_in_flight;
     const long long need = ((long long)w * local_rows + rays_per_block - 1) / rays_per_block;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, kBlock, 0, st>>>(A);
+    kern<<<(unsigned)grid, block, 0, st>>>(A);
     RRT_CU(ctx, cudaGetLastError());
     return RRT_OK;
 }

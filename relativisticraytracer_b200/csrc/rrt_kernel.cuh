@@ -57,16 +57,23 @@ namespace {
 
 
 constexpr int kTileW = 8, kTileH = 4;  // one warp = 8x4 pixels
-constexpr int kBlock = 128;
+constexpr int kBlock = 128;          // CTA size of the measured variants (rrt_variants.cuh)
+// render_kernel's warps share nothing (no shared memory, no barrier), so its CTA is ONE warp: a CTA's slot is
+// handed to the next launch the moment that warp runs out of tickets, instead of waiting for the slowest of four --
+// which is what lets the frames of a sequence overlap cleanly (rrt_set_frames_in_flight, FramePipeline).
+#ifndef RRT_RENDER_BLOCK
+#define RRT_RENDER_BLOCK 32
+#endif
+constexpr int kRenderBlock = RRT_RENDER_BLOCK;
 #ifndef RRT_MIN_BLOCKS
 #define RRT_MIN_BLOCKS 1
 #endif
-// The media variant of the render kernel is asked to fit 6 CTAs (24 warps) per SM, i.e. <= 80 registers: the
+// The media variant of the render kernel is asked to fit 24 warps per SM, i.e. <= 80 registers: the
 // out-of-line media code stalls on libdevice call chains and MUFU latency, and six warps per scheduler hide
 // that better than the four the unconstrained 109-register build gets (4K C0 78.5 -> 76.2 ms, C3 147.6 -> 135.4;
 // 7 and 8 CTAs are no better).  The geodesic-only variant needs ~72 registers anyway.
 #ifndef RRT_MIN_BLOCKS_MEDIA
-#define RRT_MIN_BLOCKS_MEDIA 6
+#define RRT_MIN_BLOCKS_MEDIA (6 * 128 / RRT_RENDER_BLOCK)
 #endif
 
 struct RayResult {
@@ -352,7 +359,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 }
 
 template <bool SPIN, bool MEDIA>
-__global__ void __launch_bounds__(kBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ FrameArgs A) {
+__global__ void __launch_bounds__(kRenderBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ FrameArgs A) {
     const int lane = threadIdx.x & 31;
     const int ntx = (A.w + kTileW - 1) / kTileW;
     const int nty = (A.local_rows + kTileH - 1) / kTileH;
