@@ -411,7 +411,7 @@ def main():
         "frac": achieved_tflops / fp32_meas,
         # DRAM bytes of one launch from the ncu --set full capture kept under profiles/ (dram__bytes_read.sum +
         # dram__bytes_write.sum; sky texels in, nothing else: the 33 MB frame stays in L2): the headline workload only
-        "traffic": 9.42e6 if (w, h, args.flags, args.camera, world) == (W4K, H4K, 3, "C0", 1) else None,
+        "traffic": 9.54e6 if (w, h, args.flags, args.camera, world) == (W4K, H4K, 3, "C0", 1) else None,
         "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
         "peak_theoretical": FP32_THEORETICAL_TFLOPS, "frac_of_theoretical": achieved_tflops / FP32_THEORETICAL_TFLOPS,
         "flop_per_step": FLOP_PER_STEP, "kernel": "render_kernel<spin,media>", "kernel_ms": kern_ms_per_step,
