@@ -1,7 +1,8 @@
 // Drop-in for the reference's include/geodesics.h: the two device functions north_star names, with the
 // reference's names and signatures, implemented by the B200 path's own device math (include/rrt_device.cuh).
-// Compile translation units that include this with nvcc -fmad=false to keep the strict rounding contract
-// (bit-identical to the reference math evaluated without FMA contraction).
+// The rounding contract follows the including translation unit (include/rrt_device.cuh): nvcc -fmad=false (default,
+// strict: bit-identical to the reference math evaluated without FMA contraction) or nvcc -fmad=true -DRRT_FMAD=1
+// (the fusion schedule of the reference's own CUDA build).
 #ifndef GEODESICS_H
 #define GEODESICS_H
 
