@@ -56,7 +56,13 @@ namespace {
 
 
 
-constexpr int kTileW = 8, kTileH = 4;  // one warp = 8x4 pixels
+constexpr int kTileW = 8, kTileH = 4;  // one warp = 8x4 pixels (measured variants)
+// render_kernel's own tile shape (a build-time experiment knob; 8x4 measured best or equal, profiles/r1_history.md)
+#ifndef RRT_TILE_W
+#define RRT_TILE_W 8
+#endif
+constexpr int kRTileW = RRT_TILE_W, kRTileH = 32 / RRT_TILE_W;
+static_assert(kRTileW * kRTileH == 32 && (kRTileW & (kRTileW - 1)) == 0, "a tile is one warp");
 constexpr int kBlock = 128;          // CTA size of the measured variants (rrt_variants.cuh)
 // render_kernel's warps share nothing (no shared memory, no barrier), so its CTA is ONE warp: a CTA's slot is
 // handed to the next launch the moment that warp runs out of tickets, instead of waiting for the slowest of four --
@@ -361,8 +367,8 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 template <bool SPIN, bool MEDIA>
 __global__ void __launch_bounds__(kRenderBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : RRT_MIN_BLOCKS) render_kernel(const __grid_constant__ FrameArgs A) {
     const int lane = threadIdx.x & 31;
-    const int ntx = (A.w + kTileW - 1) / kTileW;
-    const int nty = (A.local_rows + kTileH - 1) / kTileH;
+    const int ntx = (A.w + kRTileW - 1) / kRTileW;
+    const int nty = (A.local_rows + kRTileH - 1) / kRTileH;
     const unsigned ntiles = (unsigned)(ntx * nty);
     unsigned long long c_steps = 0, c_disk = 0, c_dust = 0, c_dense = 0;
     unsigned c_cap = 0, c_esc = 0, c_exh = 0, c_touch = 0;
@@ -379,8 +385,8 @@ __global__ void __launch_bounds__(kRenderBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : R
         int ty;
         if (k <= 2 * m) ty = (k & 1) ? c + ((k + 1) >> 1) : c - (k >> 1);
         else ty = (c > nty - 1 - c) ? (c - m - 1) - (k - (2 * m + 1)) : (c + m + 1) + (k - (2 * m + 1));
-        const int x = tx * kTileW + (lane & (kTileW - 1));
-        const int ly = ty * kTileH + (lane >> 3);
+        const int x = tx * kRTileW + (lane & (kRTileW - 1));
+        const int ly = ty * kRTileH + lane / kRTileW;
         if (x >= A.w || ly >= A.local_rows) continue;
         const int grp = ly / A.band_group;
         const int y = (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
