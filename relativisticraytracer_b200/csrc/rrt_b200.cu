@@ -214,7 +214,7 @@ extern "C" {
 int rrt_abi_version(void) { return RRT_ABI_VERSION; }
 
 const char* rrt_build_info(void) {
-    return "librrt_b200 abi=1 arch=sm_100a default kernels: fmad=false prec-div=true prec-sqrt=true ftz=false; RRT_FLAG_FMAD kernels: fmad=true (nvcc "
+    return "librrt_b200 abi=1 arch=sm_100a prec-div=true prec-sqrt=true ftz=false; RRT_FLAG_FMAD (default contract) kernels: fmad=true, strict kernels: fmad=false (nvcc "
 #define RRT_STR2(x) #x
 #define RRT_STR(x) RRT_STR2(x)
            RRT_STR(__CUDACC_VER_MAJOR__) "." RRT_STR(__CUDACC_VER_MINOR__) ")";
