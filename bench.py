@@ -116,11 +116,13 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_run(w, h, repeats=1):
-    """The reference's own CPU implementation of the path (oracle/_ref when it was built, else the port),
-    all host threads, on a w x h sample of the bench camera/parameters.  Returns (steps, best_seconds, meta)."""
+    """The reference's own CPU implementation of the path, all host threads, on a w x h sample of the bench
+    camera/parameters.  Preference: the reference headers built -O3 -mavx2 -mfma with contraction (the fastest honest CPU
+    build, when the host has AVX2+FMA), else the same headers built -O2 -ffp-contract=off, else the plain-C port.
+    Returns (steps, best_seconds, meta)."""
     from oracle import Oracle, available
     import relativisticraytracer_b200 as rrt
-    kind = "reference" if available("reference") else "port"
+    kind = "reference_fast" if available("reference_fast") else ("reference" if available("reference") else "port")
     ora = Oracle(kind, auto_build=(kind == "port"))
     prm = ora.default_params(spin_a=SPIN)
     cam = ora.camera_from(CAM_POS, CAM_YAW, CAM_PITCH)
@@ -132,9 +134,10 @@ def cpu_reference_run(w, h, repeats=1):
         f = ora.render(prm, cam, fx, sky, TIME, w, h)
         best = min(best, time.perf_counter() - t0)
         steps = f.counters["rk4_steps"]
-    return steps, best, {"kind": kind, "cores": ora.num_threads(),
-                         "sample": f"{w}x{h} frame of the bench camera/params (a=0.99 disk+dust), "
-                                   f"g++ -O2 -ffp-contract=off, OpenMP dynamic rows"}
+    flags = {"reference_fast": "reference headers, g++ -O3 -mavx2 -mfma -ffp-contract=fast",
+             "reference": "reference headers, g++ -O2 -ffp-contract=off", "port": "plain-C port, gcc -O2 -ffp-contract=off"}[kind]
+    return steps, best, {"kind": "port" if kind == "port" else "reference", "cores": ora.num_threads(),
+                         "sample": f"{w}x{h} frame of the bench camera/params (a=0.99 disk+dust), {flags}, OpenMP dynamic rows"}
 
 
 def run_reference_arm(args):

@@ -84,9 +84,10 @@ def _ptr(a):
 
 def build(kind: str = "port", quiet: bool = True) -> str:
     """Compile the requested checker with oracle/Makefile; returns the library path."""
-    target = {"port": "port", "reference": "ref", "reference_cuda": "ref_cuda"}[kind]
+    target = {"port": "port", "reference": "ref", "reference_fast": "ref_fast", "reference_cuda": "ref_cuda"}[kind]
     path = {"port": os.path.join(HERE, "librrt_oracle.so"),
             "reference": os.path.join(HERE, "_ref", "libref_host.so"),
+            "reference_fast": os.path.join(HERE, "_ref", "libref_host_fast.so"),
             "reference_cuda": os.path.join(HERE, "_ref", "libref_cuda.so")}[kind]
     if kind != "port" and not os.path.isdir(os.path.join(REF_TREE, "include")):
         if os.path.exists(path):
@@ -100,9 +101,26 @@ def build(kind: str = "port", quiet: bool = True) -> str:
     return path
 
 
+def _cpu_has(*flags) -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    have = set(line.split(":", 1)[1].split())
+                    return all(x in have for x in flags)
+    except OSError:
+        pass
+    return False
+
+
 def available(kind: str) -> bool:
+    """"reference_fast" = the reference headers built -O3 -mavx2 -mfma with contraction (timing baseline only, never
+    a parity witness); it is reported available only on a host CPU that has AVX2 and FMA."""
     path = {"port": os.path.join(HERE, "librrt_oracle.so"),
-            "reference": os.path.join(HERE, "_ref", "libref_host.so")}[kind]
+            "reference": os.path.join(HERE, "_ref", "libref_host.so"),
+            "reference_fast": os.path.join(HERE, "_ref", "libref_host_fast.so")}[kind]
+    if kind == "reference_fast" and not _cpu_has("avx2", "fma"):
+        return False
     return os.path.exists(path)
 
 
@@ -110,10 +128,11 @@ class Oracle:
     """One of the two CPU checkers behind the oracle ABI."""
 
     def __init__(self, kind: str = "port", auto_build: bool = True):
-        assert kind in ("port", "reference")
+        assert kind in ("port", "reference", "reference_fast")
         self.kind = kind
         self.prefix = "ora_" if kind == "port" else "ref_"
-        path = os.path.join(HERE, "librrt_oracle.so") if kind == "port" else os.path.join(HERE, "_ref", "libref_host.so")
+        path = {"port": os.path.join(HERE, "librrt_oracle.so"), "reference": os.path.join(HERE, "_ref", "libref_host.so"),
+                "reference_fast": os.path.join(HERE, "_ref", "libref_host_fast.so")}[kind]
         if auto_build:
             try:
                 path = build(kind)
