@@ -88,3 +88,27 @@ def test_band_rows_host_logic(built):
                 assert max_band_rows(nranks, group, h) >= (h + nranks - 1) // nranks
     assert lib.rrt_band_rows(C.byref(_capi.Band(2, 2, 8)), 100) == _capi.ERR_BAD_ARG
     assert lib.rrt_band_rows(None, 100) == 100
+
+
+def test_header_is_plain_c(built, tmp_path):
+    """include/rrt.h is the FFI surface: it must compile as strict C11 (no C++-isms, no CUDA types) and link against
+    the library from a C translation unit."""
+    src = tmp_path / "use_rrt.c"
+    src.write_text(
+        '#include "rrt.h"\n'
+        "#include <stdio.h>\n"
+        "int main(void) {\n"
+        "    rrt_params p; rrt_effects e; rrt_camera c; float pos[3] = {0.0f, 10.0f, -60.0f};\n"
+        "    rrt_default_params(&p); rrt_default_effects(&e); rrt_camera_from(pos, 0.0f, -10.0f, &c);\n"
+        '    printf("%d %d %u %.3f %d %s\\n", rrt_abi_version(), p.max_steps, p.flags, c.forward[2], rrt_path_count(), rrt_path_name(0));\n'
+        "    return sizeof(rrt_camera) == 48 && sizeof(rrt_effects) == 36 && sizeof(rrt_params) == 64 ? 0 : 1;\n"
+        "}\n")
+    from relativisticraytracer_b200 import _capi
+    pkg = os.path.dirname(_capi.LIB_PATH)
+    exe = str(tmp_path / "use_rrt")
+    res = subprocess.run(["gcc", "-std=c11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                          str(src), "-o", exe, "-L" + pkg, "-lrrt_b200", "-Wl,-rpath," + pkg], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0
+    assert out.stdout.split()[:3] == ["1", "2000", "7"] and "Gargantua" in out.stdout
