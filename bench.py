@@ -115,19 +115,41 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU arm may use: every core this process is allowed on (launchers such as torchrun export
+    OMP_NUM_THREADS=1, which says nothing about the box)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+_ORACLE = {}
+
+
+def cpu_oracle():
+    """The reference's own CPU implementation of the path behind the oracle ABI.  Preference: the reference headers built
+    -O3 -mavx2 -mfma with contraction (the fastest honest CPU build, when the host has AVX2+FMA), else the same headers
+    built -O2 -ffp-contract=off, else the plain-C port.  The OpenMP team is set explicitly to every host core."""
+    if "ora" not in _ORACLE:
+        from oracle import Oracle, available
+        kind = "reference_fast" if available("reference_fast") else ("reference" if available("reference") else "port")
+        ora = Oracle(kind, auto_build=(kind == "port"))
+        ora.set_num_threads(host_threads())
+        _ORACLE["ora"], _ORACLE["kind"] = ora, kind
+    return _ORACLE["ora"], _ORACLE["kind"]
+
+
 def cpu_reference_run(w, h, repeats=1):
-    """The reference's own CPU implementation of the path, all host threads, on a w x h sample of the bench
-    camera/parameters.  Preference: the reference headers built -O3 -mavx2 -mfma with contraction (the fastest honest CPU
-    build, when the host has AVX2+FMA), else the same headers built -O2 -ffp-contract=off, else the plain-C port.
-    Returns (steps, best_seconds, meta)."""
-    from oracle import Oracle, available
+    """One w x h sample frame of the bench camera/parameters on the host cores.  Returns (steps, best_seconds, meta)."""
     import relativisticraytracer_b200 as rrt
-    kind = "reference_fast" if available("reference_fast") else ("reference" if available("reference") else "port")
-    ora = Oracle(kind, auto_build=(kind == "port"))
+    ora, kind = cpu_oracle()
     prm = ora.default_params(spin_a=SPIN)
     cam = ora.camera_from(CAM_POS, CAM_YAW, CAM_PITCH)
     fx = ora.default_effects()
-    sky = rrt.procedural_sky(4096, 2048)
+    if "sky" not in _ORACLE:
+        _ORACLE["sky"] = rrt.procedural_sky(4096, 2048)
+    sky = _ORACLE["sky"]
     best, steps = 1e30, 0
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -140,16 +162,31 @@ def cpu_reference_run(w, h, repeats=1):
                          "sample": f"{w}x{h} frame of the bench camera/params (a=0.99 disk+dust), {flags}, OpenMP dynamic rows"}
 
 
+REFERENCE_ARM_BUDGET_S = 100.0   # wall-time bound of the whole --impl reference run (warm-up + timed steps)
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU path on the host cores; rank 0 only."""
+    """--impl reference: the reference's CPU path on the host cores; rank 0 only (the other ranks exit at once).
+    Each step is one sample frame of the bench workload (same camera, parameters, media, effects and sky; steps/s is
+    resolution-invariant to ~0.1 %).  The sample resolution is chosen from a 0.1-s calibration frame so
+    that the whole run stays under REFERENCE_ARM_BUDGET_S whatever --steps/--warmup and core count are."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    t_start = time.perf_counter()
+    cpu_reference_run(160, 90)                                   # page the library in, spin the team up
+    steps_c, dt_c, _ = cpu_reference_run(320, 180, repeats=2)
+    per_pixel = dt_c / (320 * 180)
+    n_frames = max(args.steps, 1) + max(args.warmup, 0)
     w, h = CPU_SAMPLE
+    for cand in [(1280, 720), (960, 540), (640, 360), (480, 270), (320, 180)]:
+        w, h = cand
+        if per_pixel * w * h * n_frames <= REFERENCE_ARM_BUDGET_S - 10.0:
+            break
     for _ in range(args.warmup):
         cpu_reference_run(w, h)
     tot_t, steps = 0.0, 0
-    for _ in range(args.steps):
+    for _ in range(max(args.steps, 1)):
         steps, dt, meta = cpu_reference_run(w, h)
         tot_t += dt
     per = tot_t / max(args.steps, 1)
@@ -158,7 +195,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "geodesic_rk4_steps_per_s", "value": value, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": meta["sample"]},
+        "config": {"workload": WORKLOAD, "sample": meta["sample"], "sample_width": w, "sample_height": h,
+                   "sample_note": "each step traces a bounded sample frame of the same camera/params instead of the 4K frame; "
+                                  "steps/s is resolution-invariant (SURVEY.md 8d), so the unit compares like for like",
+                   "rk4_steps_per_sample": steps, "host_threads": meta["cores"], "wall_s": time.perf_counter() - t_start},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": meta["cores"], "kind": meta["kind"],
                          "sample": meta["sample"]},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -261,6 +301,7 @@ def main():
             "C2": ((35.0, 0.8, 10.0), -106.0, -1.2), "C3": ((4.2, 0.6, 4.2), -90.0, -5.7)}
     cam = rrt.camera_state_from(*cams[args.camera])
     fx = rrt.default_effects()
+    headline = (w, h, args.flags & 3, args.camera, args.strict) == (W4K, H4K, 3, "C0", False)
     from relativisticraytracer_b200.parallel import BandedFrame
     bf = BandedFrame(r, w, h, BAND_GROUP)
     host_frame = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
@@ -353,19 +394,24 @@ def main():
         share = args.share if args.share > 0 else 1
         schedule_how = "fixed by --depth/--share"
     else:
+        # trials of PICK_FRAMES frames each (short ones are noise-limited: 8-frame trials 1.5 % apart once picked the
+        # slower schedule); the default "2 frames on the whole GPU" is kept unless the alternative is > 3 % faster
         cands = [(2, 1), (4, 2)]
+        PICK_FRAMES = 24 if world > 1 else 12
         trial = []
         for d_, s_ in cands:
             pp = FramePipeline(r, w, h, BAND_GROUP, depth=d_, to_host=False)
             timed_sequence(pp, s_, d_)                                     # warm the streams / buffers
-            ms, _, _ = timed_sequence(pp, s_, 8)
+            ms, _, _ = timed_sequence(pp, s_, PICK_FRAMES)
             tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            trial.append(float(tm.item()) / 8)
+            trial.append(float(tm.item()) / PICK_FRAMES)
             del pp
-        depth, share = cands[min(range(len(cands)), key=lambda i: trial[i])]
-        schedule_how = "auto: " + ", ".join(f"depth {d_} on 1/{s_} of the CTA slots = {t_:.2f} ms/frame" for (d_, s_), t_ in zip(cands, trial))
+        pick = 1 if trial[1] < 0.97 * trial[0] else 0
+        depth, share = cands[pick]
+        schedule_how = (f"auto ({PICK_FRAMES}-frame trials, alternative must win by > 3 %): " +
+                        ", ".join(f"depth {d_} on 1/{s_} of the CTA slots = {t_:.2f} ms/frame" for (d_, s_), t_ in zip(cands, trial)))
     pipe_dev = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=False)
     pipe_host = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=True)
 
@@ -406,15 +452,25 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (render_kernel): FP32 FMA pipe -------------------------------
+    traffic = {"bytes": None, "source": "no ncu capture for this workload (see profiles/)"}
+    if headline and world == 1:
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = {"bytes": float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"]),
+                       "source": f"{tj['capture']} (dram__bytes_read.sum + dram__bytes_write.sum of one render_kernel launch, "
+                                 f"ncu --set full, {tj['when']}); not measured by this run"}
+        except (OSError, KeyError, ValueError):
+            pass
     fp32_meas, _ = r.fp32_peak(4096)
     kern_steps_per_s = (rk4_per_frame / world) / (kern_ms_per_step * 1e-3)      # this rank's kernel (max over ranks time)
     achieved_tflops = FLOP_PER_STEP * kern_steps_per_s / 1e12
     roofline = {
         "bound": "fp32_fma", "achieved": achieved_tflops, "peak": fp32_meas, "unit": "TFLOP/s",
         "frac": achieved_tflops / fp32_meas,
-        # DRAM bytes of one launch from the ncu --set full capture kept under profiles/ (dram__bytes_read.sum +
-        # dram__bytes_write.sum; sky texels in, nothing else: the 33 MB frame stays in L2): the headline workload only
-        "traffic": 9.54e6 if (w, h, args.flags, args.camera, world) == (W4K, H4K, 3, "C0", 1) else None,
+        # DRAM bytes of one launch: not measurable from inside this process; the number is read from the committed
+        # ncu --set full capture of this same command (profiles/ncu_traffic.json names the capture), headline workload only
+        "traffic": traffic["bytes"], "traffic_source": traffic["source"],
         "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
         "peak_theoretical": FP32_THEORETICAL_TFLOPS, "frac_of_theoretical": achieved_tflops / FP32_THEORETICAL_TFLOPS,
         "flop_per_step": FLOP_PER_STEP, "kernel": "render_kernel<spin,media>", "kernel_ms": kern_ms_per_step,
@@ -425,8 +481,10 @@ def main():
         "metric": "geodesic_rk4_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if (w, h, args.flags, args.camera) == (W4K, H4K, 3, "C0") else f"EXPERIMENT {w}x{h} flags={args.flags} camera={args.camera} variant of: {WORKLOAD}",
-                   "width": w, "height": h, "spin_a": SPIN, "media": "disk+dust", "camera": "C0", "band_group_rows": BAND_GROUP,
+        "config": {"workload": WORKLOAD if headline else f"EXPERIMENT {w}x{h} flags={args.flags} camera={args.camera} variant of: {WORKLOAD}",
+                   "width": w, "height": h, "spin_a": SPIN,
+                   "media": {0: "none (geodesic only)", 1: "disk", 2: "dust", 3: "disk+dust"}[args.flags & 3], "camera": args.camera,
+                   "band_group_rows": BAND_GROUP,
                    "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) before every frame",
                    "frames_in_flight": depth, "cta_slots_per_frame": f"1/{share}", "schedule": schedule_how,
                    "rounding_contract": ("strict: unfused mul+add, the twin of the reference headers on a host" if args.strict else

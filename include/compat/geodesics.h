@@ -1,8 +1,9 @@
 // Drop-in for the reference's include/geodesics.h: the two device functions north_star names, with the
 // reference's names and signatures, implemented by the B200 path's own device math (include/rrt_device.cuh).
-// The rounding contract follows the including translation unit (include/rrt_device.cuh): nvcc -fmad=false (default,
-// strict: bit-identical to the reference math evaluated without FMA contraction) or nvcc -fmad=true -DRRT_FMAD=1
-// (the fusion schedule of the reference's own CUDA build).
+// These are header-only device functions, so their rounding contract is the INCLUDING translation unit's
+// (include/rrt_device.cuh): compile it -fmad=false without RRT_FMAD for the strict contract (bit-identical to the
+// reference math evaluated without FMA contraction), or -fmad=true -DRRT_FMAD=1 for the fusion schedule of the
+// reference's own CUDA build -- the contract librrt_b200.so's launch_raymarch / rrt_default_params use by default.
 #ifndef GEODESICS_H
 #define GEODESICS_H
 

@@ -20,8 +20,9 @@ static_assert(sizeof(CameraState) == 48, "CameraState must stay four packed floa
 
 // Renders one w x h frame into the caller-owned device buffer d_out (uchar4, pixel (x,y) stored at
 // [(h-1-y)*w + x]) on the legacy default stream, asynchronously, exactly like the reference launcher.
-// Tuning comes from the config.h this translation unit's library was built with (rrt_default_params,
-// SPIN_A from RRT_COMPAT_SPIN_A / rrt_compat_set_params); errors are swallowed to keep `void`.
+// Tuning: the macros of include/compat/config.h as they were when librrt_b200.so was built (csrc/rrt_compat.cu copies
+// them into the run-time parameter block; SPIN_A from -DRRT_COMPAT_SPIN_A), until rrt_compat_set_params replaces
+// that block at run time; errors are swallowed to keep `void`.
 void launch_raymarch(uchar4* d_out, int w, int h, float time, CameraState cam, cudaTextureObject_t skyboxTex,
                      CameraEffects effects);
 

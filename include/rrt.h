@@ -243,8 +243,8 @@ int rrt_fp32_peak_probe(rrt_context* ctx, int iters, double* tflops, double* ms)
 int rrt_exact_math_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_t* div_mismatches,
                             uint64_t* sqrt_mismatches);
 
-/* Rounding contract of the probes that take no rrt_params (hash31 / noise3D / fbm): 0 strict (default), 1 the
- * RRT_FLAG_FMAD contract.  The other probes and rrt_render follow rrt_params.flags. */
+/* Rounding contract of the probes that take no rrt_params (hash31 / noise3D / fbm): 1 the RRT_FLAG_FMAD contract
+ * (default, like rrt_default_params), 0 strict.  The other probes and rrt_render follow rrt_params.flags. */
 int rrt_set_probe_contract(rrt_context* ctx, int fmad);
 
 #ifdef __cplusplus

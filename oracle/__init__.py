@@ -151,6 +151,7 @@ class Oracle:
         self._fn("default_params").argtypes = [P(Params)]
         self._fn("default_effects").argtypes = [P(Effects)]
         self._fn("num_threads").restype = C.c_int
+        self._fn("set_num_threads").argtypes = [C.c_int]
         self._fn("camera_from").argtypes = [P(C.c_float * 3), C.c_float, C.c_float, P(Camera)]
         self._fn("path_state").argtypes = [C.c_int, C.c_float, P(Camera), vp]
         self._fn("path_state").restype = C.c_int
@@ -196,6 +197,10 @@ class Oracle:
 
     def num_threads(self) -> int:
         return int(self._fn("num_threads")())
+
+    def set_num_threads(self, n: int) -> None:
+        """OpenMP team of the next render; launchers such as torchrun export OMP_NUM_THREADS=1."""
+        self._fn("set_num_threads")(int(n))
 
     def camera_from(self, pos, yaw_deg, pitch_deg) -> Camera:
         cam = Camera()
@@ -327,3 +332,69 @@ class RefCuda:
         if rc != 0:
             raise RuntimeError(f"refcuda_render rc={rc}")
         return out, float(best.value), float(mean.value)
+
+
+class RefCudaPlanes:
+    """The INSTRUMENTED build of the reference's own CUDA kernel (oracle/ref_cuda_planes_prelude.h force-included in
+    front of the unmodified src/raymarcher.cu, same nvcc flags as RefCuda): besides the uchar4 frame it returns the
+    kernel's internal locals -- final_hdr, vel, p, intensity, hit_horizon, step count -- at float precision.
+    Needs a GPU.  spin must be 0.0 or 0.99 (compile-time there)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libref_cuda_planes.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        vp = C.c_void_p
+        self.lib.refcudap_render.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, C.c_int, C.c_int,
+                                             vp, vp, vp, vp, vp, vp, vp]
+        self.lib.refcudap_render.restype = C.c_int
+        self.lib.refcudap_probe.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, vp]
+        self.lib.refcudap_probe.restype = C.c_int
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_cuda_planes.so"))
+
+    def render(self, spin: float, cam, fx, sky: np.ndarray, time: float, w: int, h: int) -> dict:
+        """dict(rgba [h,w,4] u8 row-flipped like the reference store; hdr/vel/pos/emis [h,w,4] f32, hit [h,w] u8,
+        steps [h,w] i32, all indexed [y][x]); plus derived cls (captured / disk-hit / escaped, SURVEY.md 8a notes:
+        disk-hit := not captured and transmittance < 1) and dir = vel / |vel| in float64 -> float32."""
+        assert spin in (0.0, 0.99)
+        sky = np.ascontiguousarray(sky, dtype=np.uint8)
+        cam12 = np.frombuffer(bytes(cam), dtype=np.float32).copy()
+        fx_i = np.array([fx.use_bloom, fx.use_vignette, fx.use_ca, fx.use_lens], np.int32)
+        fx_f = np.array([fx.bloom_threshold, fx.bloom_intensity, fx.vignette_intensity, fx.ca_amount,
+                         fx.distortion_amount], np.float32)
+        o = {"rgba": np.zeros((h, w, 4), np.uint8), "hdr": np.zeros((h, w, 4), np.float32),
+             "vel": np.zeros((h, w, 4), np.float32), "pos": np.zeros((h, w, 4), np.float32),
+             "emis": np.zeros((h, w, 4), np.float32), "hit": np.zeros((h, w), np.uint8), "steps": np.zeros((h, w), np.int32)}
+        rc = self.lib.refcudap_render(1 if spin != 0.0 else 0, w, h, float(time), _ptr(cam12), _ptr(fx_i), _ptr(fx_f),
+                                      _ptr(sky), sky.shape[1], sky.shape[0], _ptr(o["rgba"]), _ptr(o["hdr"]), _ptr(o["vel"]),
+                                      _ptr(o["pos"]), _ptr(o["emis"]), _ptr(o["hit"]), _ptr(o["steps"]))
+        if rc != 0:
+            raise RuntimeError(f"refcudap_render rc={rc}")
+        captured = o["hit"] != 0
+        touched = ~captured & (o["hdr"][..., 3] < 1.0)
+        o["cls"] = np.where(captured, CLS_CAPTURED, np.where(touched, CLS_DISK_HIT, CLS_ESCAPED)).astype(np.uint8)
+        v = o["vel"][..., :3].astype(np.float64)
+        n = np.linalg.norm(v, axis=-1, keepdims=True)
+        d = np.zeros((h, w, 4), np.float32)
+        d[..., :3] = np.where(captured[..., None], 0.0, v / np.maximum(n, 1e-30))
+        o["dir"] = d
+        return o
+
+    PROBES = {"disk_density": 0, "dust_density": 1, "redshift": 2, "disk_temperature": 3, "noise3d": 4, "fbm5": 5}
+
+    def probe(self, what: str, spin: float, a, b=None, time: float = 0.0) -> np.ndarray:
+        """One of the reference's device functions as nvcc compiles it (same flags as the kernel)."""
+        assert spin in (0.0, 0.99)
+        a = _f32(a)
+        n = len(a)
+        bb = _f32(b) if b is not None else None
+        out = np.empty(n, np.float32)
+        rc = self.lib.refcudap_probe(1 if spin != 0.0 else 0, self.PROBES[what], n, _ptr(a), _ptr(bb) if bb is not None else None,
+                                     float(time), _ptr(out))
+        if rc != 0:
+            raise RuntimeError(f"refcudap_probe rc={rc}")
+        return out

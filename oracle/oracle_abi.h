@@ -107,6 +107,7 @@ typedef struct ora_counters {
 void ORA_FN(default_params)(ora_params* out);
 void ORA_FN(default_effects)(ora_effects* out);
 int ORA_FN(num_threads)(void);
+void ORA_FN(set_num_threads)(int n);
 
 /* CameraController::getCUDAStateFrom, src/main.cpp:141-167 (angles in degrees). */
 void ORA_FN(camera_from)(const float pos[3], float yaw_deg, float pitch_deg, ora_camera* out);

@@ -301,6 +301,14 @@ int ref_num_threads(void) {
     return 1;
 #endif
 }
+/* Size of the OpenMP team of the next render (launchers such as torchrun export OMP_NUM_THREADS=1). */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 void ref_camera_from(const float pos[3], float yaw_deg, float pitch_deg, ora_camera* out) {
     CameraState c = camera_from(f3(pos), yaw_deg, pitch_deg);

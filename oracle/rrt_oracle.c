@@ -462,6 +462,14 @@ int ora_num_threads(void) {
     return 1;
 #endif
 }
+/* Size of the OpenMP team of the next render (launchers such as torchrun export OMP_NUM_THREADS=1). */
+void ora_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 void ora_camera_from(const float pos[3], float yaw_deg, float pitch_deg, ora_camera* out) {
     camera_from(V(pos[0], pos[1], pos[2]), yaw_deg, pitch_deg, out);

@@ -6,7 +6,8 @@
 // Where things are:
 //   include/rrt_device.cuh   device math: the two rounding contracts, geodesic RHS, RK4, noise, densities
 //   csrc/rrt_kernel.cuh      render_kernel (one 8x4 tile per persistent warp), per-ray helpers, probe kernels
-//   csrc/rrt_variants.cuh    two measured alternatives to render_kernel (RRT_KERNEL_VARIANT=2, 3)
+//   csrc/rrt_variants.cuh    two measured-and-rejected alternatives to render_kernel; only in builds made with
+//                            EXTRA=-DRRT_WITH_VARIANTS (then selectable with RRT_KERNEL_VARIANT=2, 3, strict contract)
 //   this file                band assembly, self-test / roofline probes, rrt_context, every extern "C" entry point
 //
 // Launch organisation (B200: 148 SMs, no tensor-core work on this path -- it is FP32 FMA-pipe bound):
@@ -34,7 +35,9 @@ using rrt::V3;
 using rrt::mk;
 
 #include "rrt_kernel.cuh"
+#ifdef RRT_WITH_VARIANTS
 #include "rrt_variants.cuh"   // measured alternatives to render_kernel (RRT_KERNEL_VARIANT=2, 3), strict contract only
+#endif
 
 namespace {
 
@@ -103,10 +106,14 @@ struct rrt_context {
     unsigned long long* d_counters = nullptr;
     unsigned int* d_tickets = nullptr;
     unsigned ticket_next = 0;
-    int kernel_variant = 1;  // RRT_KERNEL_VARIANT: 1 tile-per-warp (default), 2 packed f32x2, 3 wavefront-in-warp (measured alternatives)
+    int kernel_variant = 1;  // 1 tile-per-warp (the product); 2 / 3 only in -DRRT_WITH_VARIANTS builds (RRT_KERNEL_VARIANT)
+    // launch configuration of every render kernel seen so far (resident CTAs per SM, carve-out applied): queried once
+    struct LaunchCfg { const void* kern; int per_sm; };
+    LaunchCfg launch_cfg[16] = {};
+    int n_launch_cfg = 0;
     void* d_frame[RRT_HOST_SLOTS] = {};  // device frames behind the host-destination calls, one per slot
     size_t d_frame_bytes[RRT_HOST_SLOTS] = {};
-    bool probe_fmad = false;  // contract of the parameter-less probes (hash31 / noise3D / fbm)
+    bool probe_fmad = true;   // contract of the parameter-less probes (hash31 / noise3D / fbm): like rrt_default_params
     int frames_in_flight = 1; // render launches expected to run concurrently: each gets 1/n of the resident-CTA slots
     std::string err;
     std::mutex mu;
@@ -237,10 +244,12 @@ int rrt_context_create(int device, rrt_context** out) {
     if (!ctx) return fail(nullptr, RRT_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+#ifdef RRT_WITH_VARIANTS
     if (const char* kv = std::getenv("RRT_KERNEL_VARIANT")) {
         const int k = std::atoi(kv);
         if (k >= 1 && k <= 3) ctx->kernel_variant = k;
     }
+#endif
     DevGuard g(device);
     if ((e = cudaMalloc(&ctx->d_counters, sizeof(rrt_counters))) != cudaSuccess ||
         (e = cudaMemset(ctx->d_counters, 0, sizeof(rrt_counters))) != cudaSuccess ||
@@ -393,22 +402,31 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     const bool media = (prm->flags & (RRT_FLAG_DISK | RRT_FLAG_DUST)) != 0;
     const bool fmad = (prm->flags & RRT_FLAG_FMAD) != 0;
     const rrtk::KernelSet* ks = fmad ? rrtk::rrt_kernels_fmad() : rrtk::rrt_kernels_strict();
-    // 1 (default): one tile per warp; 2: two rays per thread (f32x2); 3: wavefront in a warp.  The measured
-    // alternatives 2 and 3 exist in strict arithmetic only.
-    const int variant = fmad ? 1 : ctx->kernel_variant;
-    void (*kern)(const FrameArgs);
+    void (*kern)(const FrameArgs) = ks->render[spin ? 1 : 0][media ? 1 : 0];
+    int variant = 1;
+#ifdef RRT_WITH_VARIANTS
+    // measured alternatives (strict arithmetic only): 2 two rays per thread (f32x2), 3 wavefront in a warp
+    variant = fmad ? 1 : ctx->kernel_variant;
     if (variant == 2) kern = spin ? (media ? render_kernel2<true, true> : render_kernel2<true, false>)
                                   : (media ? render_kernel2<false, true> : render_kernel2<false, false>);
     else if (variant == 3) kern = spin ? (media ? render_kernel3<true, true> : render_kernel3<true, false>)
                                        : (media ? render_kernel3<false, true> : render_kernel3<false, false>);
-    else kern = ks->render[spin ? 1 : 0][media ? 1 : 0];
+#endif
     if ((long long)w * local_rows > (1ll << 30)) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render: band larger than 2^30 pixels");
-    // the job rings of render_kernel3 want the large shared-memory carve-out (43 KB per CTA, 5 CTAs per SM)
-    RRT_CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
     const int block = variant == 1 ? kRenderBlock : kBlock;
-    RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0));
-    if (per_sm < 1) per_sm = 1;
+    // Resident CTAs per SM and the shared-memory carve-out are properties of (kernel, device): asked for once per
+    // context, not per frame.  The carve-out stays at the shared-memory end although render_kernel declares no shared
+    // memory: every resident CTA still reserves 1 KB of it, and with one-warp CTAs (24-32 per SM) a small carve-out
+    // caps residency -- measured with cudaSharedmemCarveoutMaxL1: 4K C0 73.3 -> 80.7 ms, C3 133 -> 164 ms.
+    int per_sm = 0;
+    for (int i = 0; i < ctx->n_launch_cfg; ++i)
+        if (ctx->launch_cfg[i].kern == (const void*)kern) per_sm = ctx->launch_cfg[i].per_sm;
+    if (per_sm == 0) {
+        RRT_CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        RRT_CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0));
+        if (per_sm < 1) per_sm = 1;
+        if (ctx->n_launch_cfg < 16) ctx->launch_cfg[ctx->n_launch_cfg++] = {(const void*)kern, per_sm};
+    }
     const long long rays_per_block = (variant == 2 ? 2 : 1) * (long long)block;
     // A persistent launch normally fills every resident-CTA slot.  When the caller keeps n frames in flight, each
     // launch takes 1/n of the slots so that the n kernels run side by side from the start: a launch then lasts
@@ -428,6 +446,7 @@ int rrt_render_host_async(rrt_context* ctx, const rrt_params* prm, const rrt_cam
     if (!host_rgba || w <= 0 || h <= 0 || slot < 0 || slot >= RRT_HOST_SLOTS)
         return fail(ctx, RRT_ERR_BAD_ARG, "rrt_render_host_async: bad argument");
     const size_t bytes = (size_t)w * h * 4;
+    void* d_frame = nullptr;   // this slot's device frame, read while the context lock is held
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         DevGuard g(ctx->device);
@@ -438,11 +457,12 @@ int rrt_render_host_async(rrt_context* ctx, const rrt_params* prm, const rrt_cam
             RRT_CU(ctx, cudaMalloc(&ctx->d_frame[slot], bytes));
             ctx->d_frame_bytes[slot] = bytes;
         }
+        d_frame = ctx->d_frame[slot];
     }
-    int rc = rrt_render(ctx, prm, cam, fx, sky_texture, time, w, h, nullptr, ctx->d_frame[slot], RRT_OUT_FRAME, nullptr, stream);
+    int rc = rrt_render(ctx, prm, cam, fx, sky_texture, time, w, h, nullptr, d_frame, RRT_OUT_FRAME, nullptr, stream);
     if (rc != RRT_OK) return rc;
     DevGuard g(ctx->device);
-    RRT_CU(ctx, cudaMemcpyAsync(host_rgba, ctx->d_frame[slot], bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RRT_CU(ctx, cudaMemcpyAsync(host_rgba, d_frame, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return RRT_OK;
 }
 

@@ -13,6 +13,7 @@
 #include <string>
 
 #include "../../include/rrt.h"
+#include "../../include/compat/config.h"
 #include "../../include/compat/raymarcher.h"
 
 namespace {
@@ -24,6 +25,28 @@ std::string g_err;
 }  // namespace
 
 #define RRT_EXPORT
+
+// The reference bakes include/config.h into its kernel; here the macros of include/compat/config.h (same names, same
+// values, SPIN_A overridable with -DRRT_COMPAT_SPIN_A) are the parameter block launch_raymarch uses until
+// rrt_compat_set_params replaces it -- so editing that header and rebuilding changes the frame, as in the reference.
+static void compat_default_params(rrt_params* o) {
+    rrt_default_params(o);   // flags: both media, the rounding contract of the reference's own CUDA build
+    o->spin_a = SPIN_A;
+    o->event_horizon = EVENT_HORIZON;
+    o->isco_radius = ISCO_RADIUS;
+    o->disk_out = DISK_OUT_M;
+    o->disk_h = DISK_H_M;
+    o->disk_luminosity = DISK_LUMINOSITY;
+    o->disk_opacity = DISK_OPACITY;
+    o->exposure = EXPOSURE;
+    o->cloud_h = CLOUD_H_M;
+    o->cloud_out = CLOUD_OUT_M;
+    o->cloud_opacity = CLOUD_OPACITY;
+    o->cloud_luminosity = CLOUD_LUMINOSITY;
+    o->step_size = STEP_SIZE_M;
+    o->disk_temp_ref = DISK_TEMP_REF;
+    o->max_steps = MAX_STEPS;
+}
 
 extern "C" RRT_EXPORT void rrt_compat_set_params(const rrt_params* prm) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -44,7 +67,7 @@ RRT_EXPORT void launch_raymarch(uchar4* d_out, int w, int h, float time, CameraS
             if (rrt_context_create(dev, &g_ctx[dev]) != RRT_OK) { g_err = rrt_last_error(nullptr); g_ctx[dev] = nullptr; return; }
         }
         ctx = g_ctx[dev];
-        if (g_params_set) prm = g_params; else rrt_default_params(&prm);
+        if (g_params_set) prm = g_params; else compat_default_params(&prm);
     }
     rrt_camera c;
     static_assert(sizeof(c) == sizeof(cam), "camera layouts differ");

@@ -71,6 +71,17 @@ constexpr int kBlock = 128;          // CTA size of the measured variants (rrt_v
 #define RRT_RENDER_BLOCK 32
 #endif
 constexpr int kRenderBlock = RRT_RENDER_BLOCK;
+// steps per unchecked vacuum burst of the render loop (0 = no burst code)
+#ifndef RRT_BURST_K
+#define RRT_BURST_K 8
+#endif
+// how many of those steps one trip of the burst loop holds, for the geodesic-only and for the media kernels
+#ifndef RRT_BURST_UNROLL
+#define RRT_BURST_UNROLL 4
+#endif
+#ifndef RRT_BURST_UNROLL_MEDIA
+#define RRT_BURST_UNROLL_MEDIA 1
+#endif
 #ifndef RRT_MIN_BLOCKS
 #define RRT_MIN_BLOCKS 1
 #endif
@@ -265,6 +276,16 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
     // one compare per step for "redo with the general code": smallest stage radius below acc_rmin (or NaN), or
     // the whole ray outside the fast domain (+inf: every step is redone)
     const float redo_below = fast_ok ? C.acc_rmin : __int_as_float(0x7f800000);
+#if RRT_BURST_K > 0
+    constexpr int kBurst = RRT_BURST_K, kBurstUnroll = MEDIA ? RRT_BURST_UNROLL_MEDIA : RRT_BURST_UNROLL;
+    static_assert(kBurst % kBurstUnroll == 0, "burst length must be a multiple of its unroll factor");
+    // every threshold a checked vacuum step compares a radius against from above: zones (:56-58), horizon (:47),
+    // geodesics.h:33 through the redo guard
+    const float burst_min = fmaxf(zone_rmax, fmaxf(C.horizon_r, redo_below));
+    // entry window: kBurst steps of |v| ~ 1 (1.25 allowed) must fit between the zone sphere and the escape sphere
+    const float burst_margin = 1.25f * (float)kBurst * C.h[0];
+    const float burst_lo = burst_min + burst_margin, burst_hi = 250.0f - burst_margin;
+#endif
     // Two-level loop.  The inner loop holds what (nearly) every step needs -- the branch-free RK4 step and, in
     // lock-step for the lanes that are inside a medium, the out-of-line media sample -- and nothing else; the
     // general-domain redo of a step (practically never taken) is done by the outer loop, which then re-enters,
@@ -294,11 +315,50 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 #pragma unroll 1
         while (it < max_steps) {                                                              // :41
             if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
+#if RRT_BURST_K > 0
+            // Vacuum burst.  Most steps (94 % of the headline frame's) happen outside every step-size zone, with the
+            // whole-warp step h[0] and no medium; there the horizon test (:47), the zone logic (:54-62), the media
+            // branch (:67) and the escape test (:120) are all false.  When the radius says the next kBurst steps will stay
+            // in that regime, take them straight-line with none of those checks, tracking only the smallest radius any
+            // stage or state saw and the largest state radius (FMNMX on the ALU pipe, off the FMA pipe), and validate
+            // afterwards: min >= every threshold the checks compare against, max <= 250.  If the validation fails the
+            // state is rolled back.  Either way control falls through to the checked step below, so the result is the
+            // reference's on every path -- the entry margin only decides how often a burst is wasted, never what is
+            // computed.  The block has no break / continue on purpose: it is a structured `if`, so the lanes that took
+            // it reconverge with the others before the checked step (a `continue` here left the two groups of a warp
+            // split for the rest of their rays: 4-6 % slower on the media-heavy cameras instead of faster).
+            if (r >= burst_lo && r <= burst_hi && it + kBurst < max_steps) {
+                const V3 ps = p, vs = v;
+                const float r2s = r2, rs = r;
+                float mn = r, mx = r;
+                // kBurst steps as kBurst / kBurstUnroll trips of a rolled loop: the step is ~3 KB of code, and the media
+                // kernels' instruction working set (noise, densities, libdevice) has no room for a fully unrolled burst
+#pragma unroll 1
+                for (int kb = 0; kb < kBurst / kBurstUnroll; ++kb) {
+#pragma unroll
+                    for (int ku = 0; ku < kBurstUnroll; ++ku) {
+                        const float rm = rrt::rk4_step_fast<SPIN>(C, p, v, C.h[0], C.hh[0], C.h6[0], r2, r);   // :64
+                        r2 = rrt::norm2_loop(p);
+                        r = rrt::sqrt_rn_fast(r2);                                            // :44 of the next iteration
+                        mn = fminf(mn, fminf(rm, r));
+                        mx = fmaxf(mx, r);
+                    }
+                }
+                // mn / mx include the radius of the state the checked step below starts from: its horizon test is
+                // covered too, and its own escape test will see r <= 250
+                if (mn >= burst_min && mx <= 250.0f) it += kBurst;
+                else { p = ps; v = vs; r2 = r2s; r = rs; }
+            }
+#endif
             unsigned z = 0;
             float rmin;
             q = p;
             v_in = v;
-            if (!RRT_FMAD || r < zone_rmax) {
+            // Which lanes take the general step below (step size from the zone table) and which the constant-step copy:
+            // see the `else` branch.  With bursts in a media kernel the checked vacuum step is 1 in kBurst + 1, and the
+            // instruction cache has no room for a third copy of the step next to the media code, so it uses this one.
+            constexpr bool kOneCheckedStep = !RRT_FMAD || (MEDIA && RRT_BURST_K > 0);
+            if (kOneCheckedStep || r < zone_rmax) {
                 float h = C.h[0], h6 = C.h6[0];
                 int zsel = 0;
                 if (r < zone_rmax) {  // one compare for the steps outside every zone

@@ -142,6 +142,10 @@ class FramePipeline:
         self.rows_max = max_band_rows(self.world, group, h)
         dev = renderer.device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        # one completion event per slot: recorded at the end of the slot's work, waited on before the slot's buffers are
+        # reused by a later submit() and before last_frame() hands the destination to a consumer
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.busy = [False] * depth
         root = self.rank == 0
         self.packed = [torch.zeros((self.rows_max, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if self.world > 1 else None
         self.gathered = ([torch.zeros((self.world, self.rows_max, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)]
@@ -168,6 +172,8 @@ class FramePipeline:
                 self.r.render_host_async(prm, cam, fx, sky, time, self.w, self.h, self.host_frames[k], slot=k, stream=s)
             else:
                 self.r.render(prm, cam, fx, sky, time, self.w, self.h, out=self.frames[k], stream=s)
+            self.done[k].record(s)
+            self.busy[k] = True
             return 1
         launches = 1
         with torch.cuda.stream(s):
@@ -181,7 +187,16 @@ class FramePipeline:
                     self.host_frames[k].copy_(self.frames[k], non_blocking=True)
             else:
                 dist.gather(self.packed[k], None, dst=0)
+            self.done[k].record(s)
+        self.busy[k] = True
         return launches
+
+    def wait_slot(self, k: int) -> None:
+        """Block the host until the frame last submitted to slot k is complete (its destination may then be read, and
+        the slot's buffers are free for the next submit; submits to one slot are ordered by its stream anyway)."""
+        if self.busy[k]:
+            self.done[k].synchronize()
+            self.busy[k] = False
 
     def end(self) -> None:
         """Order the current stream after every frame submitted so far (no host synchronisation)."""
@@ -190,10 +205,15 @@ class FramePipeline:
             cur.wait_stream(s)
 
     def last_frame(self):
-        """The most recently submitted frame's destination on rank 0 (host tensor if to_host, else device)."""
-        if self.rank != 0 or self.submitted == 0:
+        """The most recently submitted frame's destination on rank 0 (host tensor if to_host, else device), complete:
+        the slot's event is synchronised first, so a consumer never reads a half-copied frame.  It stays valid until
+        `depth` further submits reuse the slot."""
+        if self.submitted == 0:
             return None
         k = (self.submitted - 1) % self.depth
+        self.wait_slot(k)
+        if self.rank != 0:
+            return None
         return self.host_frames[k] if self.to_host else self.frames[k]
 
 

@@ -66,21 +66,44 @@ def test_euler_step_bit_exact(gpu, ora, spin):
     assert bits_equal(p1, p2) and bits_equal(v1, v2)
 
 
-def test_hash31_value_exact(gpu, ora):
+@pytest.fixture
+def strict_probes(gpu, ora):
+    """hash31 / noise3D / fbm take no parameter block; their contract is per context and defaults to the library's
+    default contract (FMAD, like rrt_default_params).  These tests pin the STRICT twin of the reference headers on a
+    host, which is also the oracle port's default."""
+    gpu.set_probe_contract(False)
+    ora.set_probe_contract(False)
+    yield
+    gpu.set_probe_contract(True)
+
+
+def test_hash31_value_exact(gpu, ora, strict_probes):
     p = noise_points(seed=20)
     a, b = gpu.hash31(p), ora.hash31(p)
     assert np.array_equal(a, b)   # value equality: x - trunc(x) may give +0 where fmodf gives -0
 
 
-def test_noise3d_value_exact(gpu, ora):
+def test_noise3d_value_exact(gpu, ora, strict_probes):
     p = noise_points(seed=21)
     assert np.array_equal(gpu.noise3d(p), ora.noise3d(p))
 
 
 @pytest.mark.parametrize("octaves", [1, 2, 5])
-def test_fbm_value_exact(gpu, ora, octaves):
+def test_fbm_value_exact(gpu, ora, octaves, strict_probes):
     p = noise_points(seed=22)
     assert np.array_equal(gpu.fbm(p, octaves), ora.fbm(p, octaves))
+
+
+def test_probe_default_contract_is_the_default_params_contract(gpu, ora):
+    """A caller who validates the noise probes with defaults checks the arithmetic the default render executes."""
+    import relativisticraytracer_b200 as rrt
+    assert rrt.default_params().flags & rrt.FLAG_FMAD
+    p = noise_points(seed=24)
+    ora.set_probe_contract(True)
+    try:
+        assert bits_equal(gpu.noise3d(p), ora.noise3d(p))
+    finally:
+        ora.set_probe_contract(False)
 
 
 def test_empty_batches(gpu):
@@ -90,43 +113,57 @@ def test_empty_batches(gpu):
     assert gpu.geodesic_acc(rrt.default_params(), z, z).shape == (0, 3)
 
 
+CONTRACTS = [pytest.param(3, id="strict"), pytest.param(3 | 4, id="fmad")]   # RRT_FLAG_FMAD == ORA_FLAG_FMAD == 4
+
+
+@pytest.mark.parametrize("flags", CONTRACTS)
 @pytest.mark.parametrize("spin", [0.0, 0.99])
-def test_redshift_close(gpu, ora, spin):
+def test_redshift_close(gpu, ora, spin, flags):
     import relativisticraytracer_b200 as rrt
     q, v = phase_space(seed=30)
-    pg, po = params_pair(rrt, ora, spin_a=spin)
+    pg, po = params_pair(rrt, ora, spin_a=spin, flags=flags)
     a, b = gpu.redshift(pg, q, v), ora.redshift(po, q, v)
     assert np.array_equal(a == 0, b == 0)            # the r < 2.02 gate is exact
     np.testing.assert_allclose(a, b, rtol=TRANSCENDENTAL_RTOL, atol=0)
 
 
-def test_disk_temperature_close(gpu, ora):
+@pytest.mark.parametrize("flags", CONTRACTS)
+def test_disk_temperature_close(gpu, ora, flags):
     import relativisticraytracer_b200 as rrt
     r = np.concatenate([np.linspace(5, 40, 2000), [9.999, 10.0, 10.001]]).astype(np.float32)
-    a, b = gpu.disk_temperature(rrt.default_params(flags=3), r), ora.disk_temperature(ora.default_params(), r)
+    a, b = gpu.disk_temperature(rrt.default_params(flags=flags), r), ora.disk_temperature(ora.default_params(flags=flags), r)
     assert np.array_equal(a == 0, b == 0)
     np.testing.assert_allclose(a, b, rtol=TRANSCENDENTAL_RTOL)
 
 
+# Density tolerances.  The noise lattice hash extracts the fraction of numbers ~1e4, so a one-ulp difference between
+# libdevice and glibc in atan2f / cosf / sinf / powf upstream moves a lattice value by ~1e-3 of its range; the contrast
+# shaping (pow 1.6 with gain 2.8 and 5; smoothstep then pow 4 with gain 12) then amplifies that on the few samples that sit
+# on a steep part of the curve.  Hence: the bulk (99 %) agrees to 1e-4 of the value, 99.9 % to 1e-3 (north_star's RGB
+# tolerance), and the worst sample stays within 2e-2 / 5e-2 of the value -- measured worst cases 9e-3 / 3e-2.
+@pytest.mark.parametrize("flags", CONTRACTS)
 @pytest.mark.parametrize("time", [0.0, 1.0, 12.5])
-def test_disk_density_close(gpu, ora, time):
+def test_disk_density_close(gpu, ora, time, flags):
     import relativisticraytracer_b200 as rrt
     q = disk_points(seed=40)
-    a, b = gpu.disk_density(rrt.default_params(flags=3), q, time), ora.disk_density(ora.default_params(), q, time)
+    a, b = gpu.disk_density(rrt.default_params(flags=flags), q, time), ora.disk_density(ora.default_params(flags=flags), q, time)
     assert np.array_equal(a == 0, b == 0)            # range gate is exact arithmetic
     # density = env * (0.02 + 5c): compare against the scale of the value plus the noise floor of c
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+    assert np.quantile(err, 0.99) < 1e-4, np.quantile(err, 0.99)
     assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, 0.999)
     assert err.max() < 2e-2, err.max()
 
 
+@pytest.mark.parametrize("flags", CONTRACTS)
 @pytest.mark.parametrize("time", [0.0, 1.0, 12.5])
-def test_dust_density_close(gpu, ora, time):
+def test_dust_density_close(gpu, ora, time, flags):
     import relativisticraytracer_b200 as rrt
     q = disk_points(seed=41)
-    a, b = gpu.dust_density(rrt.default_params(flags=3), q, time), ora.dust_density(ora.default_params(), q, time)
+    a, b = gpu.dust_density(rrt.default_params(flags=flags), q, time), ora.dust_density(ora.default_params(flags=flags), q, time)
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
     # a sample sitting within an ulp of the base<0.001 early-out may flip to exactly 0 on one side
     assert np.mean((a == 0) != (b == 0)) < 1e-3
+    assert np.quantile(err, 0.99) < 1e-4, np.quantile(err, 0.99)
     assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, 0.999)
     assert err.max() < 5e-2, err.max()
