@@ -58,6 +58,11 @@ def parse():
                     help="frame (default, the headline: one 4K frame cut into row bands) or path (BASELINE config 5: "
                          "the 300-frame 'Gargantua Fly-By' at 1080p, frame k on GPU k mod N, sustained frames/s)")
     ap.add_argument("--path-frames", type=int, default=300)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: how the bands reach rank 0 -- peer: every rank's kernel stores straight into rank 0's frame over "
+                         "NVLink (CUDA IPC mapping) + a 4-byte all-reduce; nccl: packed bands + NCCL gather + assemble kernel; "
+                         "auto (default): peer when the mapping can be set up, else nccl")
+    ap.add_argument("--no-path", action="store_true", help="N > 1: skip the frame-parallel camera-path sub-record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     return ap.parse_args()
@@ -266,6 +271,54 @@ def run_path_workload(args, r, sky, prm, world, rank, dev):
     print(json.dumps(line), flush=True)
 
 
+def path_subrecord(r, sky, prm, world, rank, n=48, w=1920, h=1080):
+    """The first `n` frames of the reference's 'Gargantua Fly-By' path (src/camera_paths.cpp:33-43) under the recorder's
+    1/24 s clock at 1080p, frame k rendered whole by rank k mod N, gathered to rank 0 and copied to pinned host memory in
+    frame order (PathSequence).  Timed by the host clock between barriers; three of the gathered frames are then checked
+    byte for byte against the same frames rendered by rank 0 alone.  Runs on every rank; returns the record on rank 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import relativisticraytracer_b200 as rrt
+    from relativisticraytracer_b200.parallel import PathSequence
+    fx = rrt.default_effects()
+    seq = PathSequence(r, w, h, depth=2)
+
+    class Keep:                                    # a sink that keeps the frames it is handed (rank 0)
+        def __init__(self):
+            self.frames = []
+
+        def write(self, t):
+            self.frames.append(t.clone())
+
+    seq.render(0, 2 * world * seq.depth, prm, fx, sky)                  # warm-up rounds
+    torch.cuda.synchronize()
+    dist.barrier()
+    keep = Keep()
+    t0 = time.perf_counter()
+    done, launches = seq.render(0, n, prm, fx, sky, sink=keep if rank == 0 else None)
+    torch.cuda.synchronize()
+    dist.barrier()
+    secs = time.perf_counter() - t0
+    tm = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    secs = float(tm.item())
+    if rank != 0:
+        return None
+    ok = done == n and len(keep.frames) == n
+    for k in (1, n // 2, n):
+        t = rrt.path_clock(k, 24.0)
+        cam, _ = rrt.path_state(0, t)
+        want = np.zeros((h, w, 4), np.uint8)
+        r.render_host(prm, cam, fx, sky, t, w, h, want)
+        ok = ok and bool(np.array_equal(keep.frames[k - 1].numpy(), want))
+    return {"workload": f"{n} frames of the 'Gargantua Fly-By' Catmull-Rom path at {w}x{h}, a=0.99 disk+dust, frame k on GPU k mod {world}, "
+                        "gathered to rank 0 and copied to pinned host memory in frame order",
+            "frames": n, "frames_per_s": n / secs, "seconds": secs, "frames_in_flight": seq.depth,
+            "frames_equal_single_gpu_render": ok, "gpu_launches_rank0": launches,
+            "timing": "host wall clock between barriers, max over ranks, device->host copies inside"}
+
+
 # ------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -303,7 +356,7 @@ def main():
     fx = rrt.default_effects()
     headline = (w, h, args.flags & 3, args.camera, args.strict) == (W4K, H4K, 3, "C0", False)
     from relativisticraytracer_b200.parallel import BandedFrame
-    bf = BandedFrame(r, w, h, BAND_GROUP)
+    bf = BandedFrame(r, w, h, BAND_GROUP, exchange=args.exchange)
     host_frame = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     stream = torch.cuda.current_stream()
@@ -341,6 +394,13 @@ def main():
             if world == 1:
                 launches += one_frame(to_host)
                 e1.record(stream)
+            elif bf.exchange == "peer":
+                r.render(prm, cam, fx, sky, TIME, w, h, band=bf.band, out=bf.peer)      # stores land in rank 0's frame
+                e1.record(stream)
+                launches += 1
+                dist.all_reduce(bf.token)                                               # every band has landed
+                if to_host and rank == 0:
+                    host_frame.copy_(bf.frame, non_blocking=True)
             else:
                 r.render(prm, cam, fx, sky, TIME, w, h, band=bf.band, out=bf.packed, layout=rrt.OUT_PACKED)
                 e1.record(stream)
@@ -400,7 +460,7 @@ def main():
         PICK_FRAMES = 24 if world > 1 else 12
         trial = []
         for d_, s_ in cands:
-            pp = FramePipeline(r, w, h, BAND_GROUP, depth=d_, to_host=False)
+            pp = FramePipeline(r, w, h, BAND_GROUP, depth=d_, to_host=False, exchange=bf.exchange if world > 1 else "auto")
             timed_sequence(pp, s_, d_)                                     # warm the streams / buffers
             ms, _, _ = timed_sequence(pp, s_, PICK_FRAMES)
             tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -412,8 +472,9 @@ def main():
         depth, share = cands[pick]
         schedule_how = (f"auto ({PICK_FRAMES}-frame trials, alternative must win by > 3 %): " +
                         ", ".join(f"depth {d_} on 1/{s_} of the CTA slots = {t_:.2f} ms/frame" for (d_, s_), t_ in zip(cands, trial)))
-    pipe_dev = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=False)
-    pipe_host = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=True)
+    xchg = bf.exchange if world > 1 else "auto"
+    pipe_dev = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=False, exchange=xchg)
+    pipe_host = FramePipeline(r, w, h, BAND_GROUP, depth=depth, to_host=True, exchange=xchg)
 
     # ---- warm-up, then the counted work of one step -------------------------------------------------
     timed(args.warmup, False)
@@ -445,6 +506,11 @@ def main():
     e2e_ms_per_step = e2e_ms / args.steps
     lat_ms_per_step = lat_ms / args.steps
     value = rk4_per_frame / (ms_per_step * 1e-3)
+
+    # ---- N > 1: BASELINE config 5 beside the headline (frame-parallel camera path, frame k on rank k mod N) ----------
+    path_rec = None
+    if world > 1 and not args.no_path:
+        path_rec = path_subrecord(r, sky, prm, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -485,7 +551,7 @@ def main():
                    "width": w, "height": h, "spin_a": SPIN,
                    "media": {0: "none (geodesic only)", 1: "disk", 2: "dust", 3: "disk+dust"}[args.flags & 3], "camera": args.camera,
                    "band_group_rows": BAND_GROUP,
-                   "parallelism": f"rowbands{world}", "l2": "flushed (256 MiB write) before every frame",
+                   "parallelism": f"rowbands{world}", "exchange": bf.exchange, "l2": "flushed (256 MiB write) before every frame",
                    "frames_in_flight": depth, "cta_slots_per_frame": f"1/{share}", "schedule": schedule_how,
                    "rounding_contract": ("strict: unfused mul+add, the twin of the reference headers on a host" if args.strict else
                                          "fmad: the FMA fusion schedule of the reference's own CUDA build (default)"),
@@ -497,11 +563,15 @@ def main():
                 "frames_per_s": 1e3 / e2e_ms_per_step, "ms_per_step": e2e_ms_per_step,
                 "h2d_bytes_per_step": 64 + 48 + 36 + 16, "d2h_bytes_per_step": w * h * 4,
                 "timing": "host wall clock around the K-frame sequence incl. final synchronize",
-                "path": "rrt_render_host_async (C ABI, pinned host frames)" if world == 1 else "rrt_render per rank + NCCL gather + rrt_assemble_bands + D2H to pinned host"},
+                "path": ("rrt_render_host_async (C ABI, pinned host frames)" if world == 1 else
+                         ("rrt_render per rank storing into rank 0's peer-mapped frame + 4-byte all-reduce + D2H to pinned host" if xchg == "peer"
+                          else "rrt_render per rank + NCCL gather + rrt_assemble_bands + D2H to pinned host"))},
         "gpu_launches": launches,
         "clocks": clk.summary(),
     }
 
+    if path_rec is not None:
+        line["path"] = path_rec
     if world == 1 and not args.no_cpu_baseline:
         cw, ch = CPU_SAMPLE
         steps_c, secs, meta = cpu_reference_run(cw, ch, repeats=3)     # ~15 s of host work, best of 3

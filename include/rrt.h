@@ -16,6 +16,7 @@
 #ifndef RRT_H
 #define RRT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -173,6 +174,22 @@ int rrt_band_rows(const rrt_band* band, int h);
  * row-flipped frame -- the step after the NVLink gather on the encoding GPU. */
 int rrt_assemble_bands(rrt_context* ctx, const void* d_packed, int rows_per_rank, int w, int h, int nranks,
                        int group, void* d_frame, void* stream);
+
+/* ---- peer frames: the exchange step of a band-parallel frame without a gather --------------------------------
+ * One process per GPU.  The encoding GPU's process (rank 0) creates the frame with rrt_peer_frame_create and hands
+ * the 64-byte handle to the other processes (any channel: torch.distributed, a pipe ...); they map it with
+ * rrt_peer_frame_open and pass the returned device pointer as d_out to rrt_render(band = their rows,
+ * out_layout = RRT_OUT_FRAME).  The render kernel then stores each finished pixel straight into rank 0's row-flipped
+ * frame over NVLink (4 B per ~220 kFLOP of tracing): no packed buffer, no NCCL gather, no rrt_assemble_bands --
+ * the store that ends the path (src/raymarcher.cu:168) IS the exchange (the reference's exchange point is the mapped
+ * PBO, src/main.cpp:463-469).  Ordering is the caller's: a stream-ordered barrier across the ranks (e.g. a 4-byte
+ * NCCL all-reduce enqueued after the render) tells rank 0 that every band has landed.
+ * CUDA IPC: processes must differ (a handle cannot be opened by the process that created it). */
+#define RRT_PEER_HANDLE_BYTES 64
+int rrt_peer_frame_create(rrt_context* ctx, size_t bytes, void** d_frame, uint8_t handle[RRT_PEER_HANDLE_BYTES]);
+int rrt_peer_frame_open(rrt_context* ctx, const uint8_t handle[RRT_PEER_HANDLE_BYTES], void** d_frame);
+/* owner != 0: the creating process frees the frame; owner == 0: a mapping process unmaps it */
+int rrt_peer_frame_close(rrt_context* ctx, void* d_frame, int owner);
 
 /* Synchronises the context's work, copies the counters out and optionally zeroes them. */
 int rrt_read_counters(rrt_context* ctx, rrt_counters* out, int reset);

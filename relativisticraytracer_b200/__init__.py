@@ -8,7 +8,7 @@ need a GPU, calling any render or probe entry point does.
 from ._capi import (Band, Camera, Counters, Effects, Params, Planes, RrtError, FLAG_DISK, FLAG_DUST, FLAG_FMAD, CLS_CAPTURED,
                     CLS_DISK_HIT, CLS_ESCAPED, CLS_MASK, CLSF_EXHAUSTED, CLSF_TOUCHED, OUT_FRAME, OUT_PACKED, LIB_PATH,
                     default_effects, default_params, effects_off)
-from .renderer import (CameraEffects, CameraState, Renderer, Sky, camera_state_from, launch_raymarch, path_clock,
+from .renderer import (CameraEffects, CameraState, PeerFrame, Renderer, Sky, camera_state_from, launch_raymarch, path_clock,
                        path_duration, path_names, path_state, set_launch_params)
 from .skybox import load_skybox, procedural_sky
 from .sink import FrameSink, ffmpeg_command

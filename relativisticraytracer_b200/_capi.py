@@ -75,6 +75,7 @@ SYMBOLS = [
     "rrt_disk_density_batch", "rrt_dust_density_batch", "rrt_sky_sample_batch", "rrt_fp32_peak_probe",
     "rrt_camera_from", "rrt_path_count", "rrt_path_name", "rrt_path_num_keys", "rrt_path_duration",
     "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest",
+    "rrt_peer_frame_create", "rrt_peer_frame_open", "rrt_peer_frame_close",
     "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
 ]
 
@@ -115,6 +116,9 @@ def load() -> C.CDLL:
     lib.rrt_band_rows.argtypes = [P(Band), ci]
     lib.rrt_assemble_bands.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
     lib.rrt_read_counters.argtypes = [vp, P(Counters), ci]
+    lib.rrt_peer_frame_create.argtypes = [vp, C.c_size_t, P(vp), vp]
+    lib.rrt_peer_frame_open.argtypes = [vp, vp, P(vp)]
+    lib.rrt_peer_frame_close.argtypes = [vp, vp, ci]
     lib.rrt_geodesic_acc_batch.argtypes = [vp, P(Params), ci, vp, vp, vp]
     lib.rrt_rk4_step_batch.argtypes = [vp, P(Params), ci, vp, vp, vp]
     lib.rrt_euler_step_batch.argtypes = [vp, P(Params), ci, vp, vp, vp]

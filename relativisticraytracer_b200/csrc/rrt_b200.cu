@@ -487,6 +487,44 @@ int rrt_assemble_bands(rrt_context* ctx, const void* d_packed, int rows_per_rank
     return RRT_OK;
 }
 
+int rrt_peer_frame_create(rrt_context* ctx, size_t bytes, void** d_frame, uint8_t handle[RRT_PEER_HANDLE_BYTES]) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!d_frame || !handle || bytes == 0) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_peer_frame_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RRT_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+    DevGuard g(ctx->device);
+    *d_frame = nullptr;
+    void* p = nullptr;
+    RRT_CU(ctx, cudaMalloc(&p, bytes));   // a raw allocation: an IPC handle names a whole cudaMalloc block
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(ctx, RRT_ERR_CUDA, "rrt_peer_frame_create", e); }
+    std::memcpy(handle, &h, sizeof(h));
+    *d_frame = p;
+    return RRT_OK;
+}
+
+int rrt_peer_frame_open(rrt_context* ctx, const uint8_t handle[RRT_PEER_HANDLE_BYTES], void** d_frame) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!d_frame || !handle) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_peer_frame_open: bad argument");
+    DevGuard g(ctx->device);
+    *d_frame = nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    RRT_CU(ctx, cudaIpcOpenMemHandle(d_frame, h, cudaIpcMemLazyEnablePeerAccess));
+    return RRT_OK;
+}
+
+int rrt_peer_frame_close(rrt_context* ctx, void* d_frame, int owner) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!d_frame) return RRT_OK;
+    DevGuard g(ctx->device);
+    RRT_CU(ctx, cudaDeviceSynchronize());
+    if (owner) RRT_CU(ctx, cudaFree(d_frame));
+    else RRT_CU(ctx, cudaIpcCloseMemHandle(d_frame));
+    return RRT_OK;
+}
+
 int rrt_read_counters(rrt_context* ctx, rrt_counters* out, int reset) {
     if (!ctx) return RRT_ERR_BAD_ARG;
     if (!out) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_read_counters: out is NULL");

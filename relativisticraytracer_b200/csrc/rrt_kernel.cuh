@@ -327,7 +327,15 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             // computed.  The block has no break / continue on purpose: it is a structured `if`, so the lanes that took
             // it reconverge with the others before the checked step (a `continue` here left the two groups of a warp
             // split for the rest of their rays: 4-6 % slower on the media-heavy cameras instead of faster).
-            if (r >= burst_lo && r <= burst_hi && it + kBurst < max_steps) {
+            // Warp-uniform on purpose: the burst is taken only when EVERY lane still in the loop qualifies.  A lane that
+            // burst on its own would finish its vacuum phase in 1/kBurst of the iterations -- alone, while its tile
+            // mates are still in a zone -- instead of sharing each execution of the step with the other vacuum lanes of
+            // the warp: measured with a per-lane burst, the media-heavy cameras (mixed tiles) got 2-6 % slower, not
+            // faster.  (__activemask: the vote only decides how the steps are scheduled, never what they compute.)
+            // The vote costs the iterations that cannot burst one VOTE: the lanes in the loop are counted here, the
+            // qualifying ones inside the branch, and the burst runs when the two sets are the same.
+            const unsigned in_loop = __activemask();
+            if (r >= burst_lo && r <= burst_hi && it + kBurst < max_steps && __activemask() == in_loop) {
                 const V3 ps = p, vs = v;
                 const float r2s = r2, rs = r;
                 float mn = r, mx = r;
@@ -357,7 +365,11 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             // Which lanes take the general step below (step size from the zone table) and which the constant-step copy:
             // see the `else` branch.  With bursts in a media kernel the checked vacuum step is 1 in kBurst + 1, and the
             // instruction cache has no room for a third copy of the step next to the media code, so it uses this one.
+#ifdef RRT_TWO_CHECKED   // A/B knob: keep the constant-step copy of the checked vacuum step in the media kernels too
+            constexpr bool kOneCheckedStep = !RRT_FMAD;
+#else
             constexpr bool kOneCheckedStep = !RRT_FMAD || (MEDIA && RRT_BURST_K > 0);
+#endif
             if (kOneCheckedStep || r < zone_rmax) {
                 float h = C.h[0], h6 = C.h6[0];
                 int zsel = 0;

@@ -65,6 +65,37 @@ def gather_bands(packed: torch.Tensor, dst: int = 0, group=None) -> Optional[tor
     return None
 
 
+def share_peer_frames(renderer, h: int, w: int, count: int):
+    """``count`` frames on rank 0's GPU that every rank's render kernel can store into (renderer.PeerFrame): rank 0
+    creates them, the 64-byte CUDA IPC handles travel by broadcast_object_list, the other ranks map them.  Returns the
+    list of PeerFrame objects, or None (on every rank alike) if any rank could not set the mapping up -- the caller then
+    keeps the NCCL gather path."""
+    from .renderer import PeerFrame
+    rank = dist.get_rank()
+    frames, handles, ok = [], [None] * count, 1
+    if rank == 0:
+        try:
+            frames = [PeerFrame(renderer, h, w) for _ in range(count)]
+            handles = [f.handle for f in frames]
+        except Exception:
+            ok, handles = 0, [None] * count
+    dist.broadcast_object_list(handles, src=0)
+    if rank != 0:
+        try:
+            if any(hd is None for hd in handles):
+                raise RuntimeError("rank 0 has no peer frames")
+            frames = [PeerFrame(renderer, h, w, handle=hd) for hd in handles]
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", renderer.device))
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        for f in frames:
+            f.close()
+        return None
+    return frames
+
+
 def frame_owner(frame_index: int, nranks: int) -> int:
     """Frame-parallel path rendering: frame k -> rank k % N."""
     return frame_index % nranks
@@ -94,22 +125,42 @@ def path_rounds(n_frames: int, nranks: int, first_frame: int = 1):
 class BandedFrame:
     """Buffers + calls for one banded frame on this rank (see module docstring)."""
 
-    def __init__(self, renderer, w: int, h: int, group: int = DEFAULT_GROUP):
+    def __init__(self, renderer, w: int, h: int, group: int = DEFAULT_GROUP, exchange: str = "auto"):
+        """exchange: "peer" = every rank's kernel stores straight into rank 0's frame (CUDA IPC mapping, see
+        rrt_peer_frame_*), a 4-byte all-reduce is the barrier; "nccl" = packed bands + NCCL gather + rrt_assemble_bands;
+        "auto" = peer when the mapping can be set up on every rank, else nccl."""
         self.r, self.w, self.h, self.group = renderer, w, h, group
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.band = Band(self.rank, self.world, group)
         self.rows_max = max_band_rows(self.world, group, h)
         dev = renderer.device
-        self.packed = torch.zeros((self.rows_max, w, 4), dtype=torch.uint8, device=dev)
-        self.gathered = (torch.zeros((self.world, self.rows_max, w, 4), dtype=torch.uint8, device=dev)
-                         if self.rank == 0 and self.world > 1 else None)
-        self.frame = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev) if self.rank == 0 else None
+        self.peer = None
+        if self.world > 1 and exchange in ("auto", "peer"):
+            pf = share_peer_frames(renderer, h, w, 1)
+            if pf is None and exchange == "peer":
+                raise RuntimeError("peer frames unavailable (CUDA IPC mapping failed on some rank)")
+            self.peer = pf[0] if pf else None
+        self.exchange = "peer" if self.peer is not None else ("nccl" if self.world > 1 else "none")
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.packed = self.gathered = None
+        if self.exchange == "nccl":
+            self.packed = torch.zeros((self.rows_max, w, 4), dtype=torch.uint8, device=dev)
+            self.gathered = torch.zeros((self.world, self.rows_max, w, 4), dtype=torch.uint8, device=dev) if self.rank == 0 else None
+        if self.rank == 0:
+            self.frame = self.peer.tensor if self.peer is not None else torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
+        else:
+            self.frame = None
 
     def render(self, prm, cam, fx, sky, time: float) -> int:
-        """Trace this rank's rows, gather, assemble on rank 0.  Returns how many of OUR kernels were launched."""
+        """Trace this rank's rows and bring them together on rank 0.  Returns how many of OUR kernels were launched."""
         if self.world == 1:
             self.r.render(prm, cam, fx, sky, time, self.w, self.h, out=self.frame)
+            return 1
+        if self.exchange == "peer":
+            # the store that ends the path is the exchange; the all-reduce orders rank 0's consumers after every band
+            self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.peer)
+            dist.all_reduce(self.token)
             return 1
         self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.packed, layout=OUT_PACKED)
         if self.rank == 0:
@@ -132,7 +183,8 @@ class FramePipeline:
     as in the unpipelined call, so results are identical.
     """
 
-    def __init__(self, renderer, w: int, h: int, group: int = DEFAULT_GROUP, depth: int = 2, to_host: bool = False):
+    def __init__(self, renderer, w: int, h: int, group: int = DEFAULT_GROUP, depth: int = 2, to_host: bool = False,
+                 exchange: str = "auto"):
         if not 1 <= depth <= HOST_SLOTS:
             raise ValueError(f"depth must be 1..{HOST_SLOTS}")
         self.r, self.w, self.h, self.group, self.depth, self.to_host = renderer, w, h, group, depth, to_host
@@ -147,11 +199,23 @@ class FramePipeline:
         self.done = [torch.cuda.Event() for _ in range(depth)]
         self.busy = [False] * depth
         root = self.rank == 0
-        self.packed = [torch.zeros((self.rows_max, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if self.world > 1 else None
+        # exchange step of a band-parallel frame, see BandedFrame
+        self.peer = None
+        if self.world > 1 and exchange in ("auto", "peer"):
+            self.peer = share_peer_frames(renderer, h, w, depth)
+            if self.peer is None and exchange == "peer":
+                raise RuntimeError("peer frames unavailable (CUDA IPC mapping failed on some rank)")
+        self.exchange = "peer" if self.peer is not None else ("nccl" if self.world > 1 else "none")
+        self.tokens = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(depth)]
+        nccl = self.exchange == "nccl"
+        self.packed = [torch.zeros((self.rows_max, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if nccl else None
         self.gathered = ([torch.zeros((self.world, self.rows_max, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)]
-                         if root and self.world > 1 else None)
+                         if root and nccl else None)
         need_dev_frame = root and (self.world > 1 or not to_host)
-        self.frames = [torch.zeros((h, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if need_dev_frame else None
+        if self.peer is not None:
+            self.frames = [f.tensor for f in self.peer] if root else None
+        else:
+            self.frames = [torch.zeros((h, w, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] if need_dev_frame else None
         self.host_frames = ([torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(depth)]
                             if root and to_host else None)
         self.submitted = 0
@@ -176,6 +240,19 @@ class FramePipeline:
             self.busy[k] = True
             return 1
         launches = 1
+        if self.exchange == "peer":
+            with torch.cuda.stream(s):
+                # every rank's kernel stores its rows straight into slot k of rank 0's frames; all-reduce #1 tells rank 0
+                # that all bands have landed, all-reduce #2 (after rank 0's device->host copy) tells the others that the
+                # slot may be overwritten by frame k + depth
+                self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.peer[k], stream=s)
+                dist.all_reduce(self.tokens[k])
+                if self.rank == 0 and self.to_host:
+                    self.host_frames[k].copy_(self.frames[k], non_blocking=True)
+                dist.all_reduce(self.tokens[k])
+                self.done[k].record(s)
+            self.busy[k] = True
+            return launches
         with torch.cuda.stream(s):
             self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.packed[k], layout=OUT_PACKED, stream=s)
             if self.rank == 0:

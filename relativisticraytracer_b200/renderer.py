@@ -84,6 +84,37 @@ PLANE_SPECS = {"hdr": (4, torch.float32), "dir": (4, torch.float32), "emis": (4,
                "pos": (4, torch.float32), "vel": (4, torch.float32), "cls": (0, torch.uint8), "steps": (0, torch.int32)}
 
 
+class PeerFrame:
+    """A device frame on the encoding GPU that other processes' render kernels store into directly (C ABI
+    rrt_peer_frame_*; CUDA IPC).  The owner (rank 0) creates it and passes ``handle`` (64 bytes) to the other ranks,
+    which ``open`` it; ``tensor`` (owner only) is a torch view [h, w, 4] uint8 of the same memory."""
+
+    def __init__(self, renderer: "Renderer", h: int, w: int, handle: Optional[bytes] = None):
+        self.r, self.h, self.w, self.nbytes = renderer, h, w, h * w * 4
+        self.owner = handle is None
+        ptr = C.c_void_p()
+        if self.owner:
+            buf = (C.c_uint8 * 64)()
+            renderer._check(renderer._lib.rrt_peer_frame_create(renderer._ctx, C.c_size_t(self.nbytes), C.byref(ptr), buf))
+            self.handle = bytes(buf)
+        else:
+            assert len(handle) == 64
+            self.handle = bytes(handle)
+            buf = (C.c_uint8 * 64).from_buffer_copy(self.handle)
+            renderer._check(renderer._lib.rrt_peer_frame_open(renderer._ctx, buf, C.byref(ptr)))
+        self.ptr = int(ptr.value)
+        self.tensor = None
+        if self.owner:
+            self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+            self.tensor = torch.as_tensor(self, device=torch.device("cuda", renderer.device))
+
+    def close(self):
+        if self.ptr:
+            self.tensor = None
+            self.r._lib.rrt_peer_frame_close(self.r._ctx, C.c_void_p(self.ptr), 1 if self.owner else 0)
+            self.ptr = 0
+
+
 class Renderer:
     """One rrt_context on one B200.  Thread-compatible; launches are asynchronous on the given stream."""
 
@@ -136,9 +167,14 @@ class Renderer:
         """rrt_render: one frame (or one band of it) into a device uchar4 tensor; asynchronous."""
         tex = sky.texture if isinstance(sky, Sky) else int(sky)
         rows = h if layout == OUT_FRAME else self.band_rows(band, h)
-        if out is None:
-            out = torch.empty((rows, w, 4), dtype=torch.uint8, device=self.device)
-        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= rows * w * 4
+        if isinstance(out, PeerFrame):      # a frame that lives on the encoding GPU (possibly another process's)
+            assert layout == OUT_FRAME and out.nbytes >= h * w * 4
+            out_ptr = out.ptr
+        else:
+            if out is None:
+                out = torch.empty((rows, w, 4), dtype=torch.uint8, device=self.device)
+            assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= rows * w * 4
+            out_ptr = out.data_ptr()
         pl = None
         if planes:
             pl = Planes()
@@ -149,7 +185,7 @@ class Renderer:
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         self._check(self._lib.rrt_render(self._ctx, C.byref(prm), C.byref(cam), C.byref(fx), C.c_uint64(tex),
                                          float(time), int(w), int(h), C.byref(band) if band is not None else None,
-                                         C.c_void_p(out.data_ptr()), int(layout),
+                                         C.c_void_p(out_ptr), int(layout),
                                          C.byref(pl) if pl is not None else None, C.c_void_p(st.cuda_stream)))
         return out
 

@@ -139,8 +139,9 @@ def test_disk_temperature_close(gpu, ora, flags):
 # Density tolerances.  The noise lattice hash extracts the fraction of numbers ~1e4, so a one-ulp difference between
 # libdevice and glibc in atan2f / cosf / sinf / powf upstream moves a lattice value by ~1e-3 of its range; the contrast
 # shaping (pow 1.6 with gain 2.8 and 5; smoothstep then pow 4 with gain 12) then amplifies that on the few samples that sit
-# on a steep part of the curve.  Hence: the bulk (99 %) agrees to 1e-4 of the value, 99.9 % to 1e-3 (north_star's RGB
-# tolerance), and the worst sample stays within 2e-2 / 5e-2 of the value -- measured worst cases 9e-3 / 3e-2.
+# on a steep part of the curve, more so at large `time` (the sheared angle grows).  Measured on a B200 over these inputs
+# (gpurun_out/r2_4_density_err.txt, both contracts, times 0 / 1 / 12.5): 99 % of the samples within 2.2e-5 .. 2.1e-4 of
+# the value, 99.9 % within 5.4e-5 .. 9.4e-4, worst sample 8.0e-4 (disk) / 1.3e-3 (dust).
 @pytest.mark.parametrize("flags", CONTRACTS)
 @pytest.mark.parametrize("time", [0.0, 1.0, 12.5])
 def test_disk_density_close(gpu, ora, time, flags):
@@ -150,9 +151,9 @@ def test_disk_density_close(gpu, ora, time, flags):
     assert np.array_equal(a == 0, b == 0)            # range gate is exact arithmetic
     # density = env * (0.02 + 5c): compare against the scale of the value plus the noise floor of c
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
-    assert np.quantile(err, 0.99) < 1e-4, np.quantile(err, 0.99)
+    assert np.quantile(err, 0.99) < 3e-4, np.quantile(err, 0.99)
     assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, 0.999)
-    assert err.max() < 2e-2, err.max()
+    assert err.max() < 3e-3, err.max()
 
 
 @pytest.mark.parametrize("flags", CONTRACTS)
@@ -164,6 +165,6 @@ def test_dust_density_close(gpu, ora, time, flags):
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
     # a sample sitting within an ulp of the base<0.001 early-out may flip to exactly 0 on one side
     assert np.mean((a == 0) != (b == 0)) < 1e-3
-    assert np.quantile(err, 0.99) < 1e-4, np.quantile(err, 0.99)
-    assert np.quantile(err, 0.999) < 1e-3, np.quantile(err, 0.999)
-    assert err.max() < 5e-2, err.max()
+    assert np.quantile(err, 0.99) < 3e-4, np.quantile(err, 0.99)
+    assert np.quantile(err, 0.999) < 1.5e-3, np.quantile(err, 0.999)
+    assert err.max() < 5e-3, err.max()
