@@ -31,6 +31,7 @@ extern "C" {
 #define RRT_ERR_CUDA (-2)      /* a CUDA runtime call or the kernel failed; see rrt_last_error() */
 #define RRT_ERR_NO_DEVICE (-3) /* no usable sm_100 device */
 #define RRT_ERR_NOMEM (-4)
+#define RRT_ERR_UNSUPPORTED (-6) /* a valid file this build does not decode (see rrt_image_load) */
 #define RRT_ERR_IO (-5)        /* frame sink: open / write / close failed */
 
 /* ---- parameter surface ---------------------------------------------------------------------------
@@ -137,6 +138,21 @@ void rrt_default_effects(rrt_effects* out); /* the default member initialisers o
  * with addressMode {Wrap, Clamp}, linear filter, normalised-float read, normalised coordinates. */
 int rrt_sky_create(rrt_context* ctx, const uint8_t* host_rgba, int w, int h, rrt_sky** out);
 uint64_t rrt_sky_texture(const rrt_sky* sky); /* the cudaTextureObject_t, usable with launch_raymarch */
+
+/* ---- skybox files: the host half of loadSkybox (src/main.cpp:237-245) ---------------------------------------------
+ * The reference decodes its skybox with stbi_load(path, &w, &h, &c, 4) (stb_image v2.30, vendored there).  These entry
+ * points decode PNG and baseline JPEG natively and return the SAME RGBA8 bytes stb_image returns for the file (for JPEG
+ * that means stb_image's integer IDCT, chroma upsampling filters and fixed-point YCbCr->RGB, see csrc/rrt_image.cpp),
+ * so a frame rendered from a file is the frame the reference renders from it.  Files outside that subset (progressive
+ * or CMYK JPEG, 16-bit or interlaced PNG, other formats) fail with RRT_ERR_UNSUPPORTED; unreadable or corrupt files
+ * with RRT_ERR_IO; the message is in rrt_image_last_error().  Pure host code, no device needed.
+ * rrt_image_load / rrt_image_decode allocate *rgba (w*h*4 bytes, top row first); release it with rrt_image_free.
+ * rrt_sky_load = rrt_image_load + rrt_sky_create (the whole loadSkybox). */
+int rrt_image_load(const char* path, uint8_t** rgba, int* w, int* h);
+int rrt_image_decode(const uint8_t* data, size_t size, uint8_t** rgba, int* w, int* h);
+void rrt_image_free(uint8_t* rgba);
+const char* rrt_image_last_error(void);
+int rrt_sky_load(rrt_context* ctx, const char* path, rrt_sky** out);
 void rrt_sky_destroy(rrt_sky* sky);
 
 /* ---- the hot path: replaces launch_raymarch / raymarch_kernel ------------------------------------ */

@@ -10,7 +10,7 @@ from ._capi import (Band, Camera, Counters, Effects, Params, Planes, RrtError, F
                     default_effects, default_params, effects_off)
 from .renderer import (CameraEffects, CameraState, PeerFrame, Renderer, Sky, camera_state_from, launch_raymarch, path_clock,
                        path_duration, path_names, path_state, set_launch_params)
-from .skybox import load_skybox, procedural_sky
+from .skybox import decode_image, load_skybox, procedural_sky
 from .sink import FrameSink, ffmpeg_command
 from ._capi import SINK_RGBA, SINK_Y4M, HOST_SLOTS
 

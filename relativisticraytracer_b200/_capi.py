@@ -12,7 +12,7 @@ import os
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RRT_B200_LIB") or os.path.join(PKG_DIR, "librrt_b200.so")   # env: A/B builds only
 
-OK, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_IO = 0, -1, -2, -3, -4, -5
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_NOMEM, ERR_IO, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 SINK_RGBA, SINK_Y4M = 0, 1
 FLAG_DISK, FLAG_DUST, FLAG_FMAD = 1, 2, 4
 CLS_CAPTURED, CLS_DISK_HIT, CLS_ESCAPED, CLS_MASK = 0, 1, 2, 3
@@ -75,6 +75,7 @@ SYMBOLS = [
     "rrt_disk_density_batch", "rrt_dust_density_batch", "rrt_sky_sample_batch", "rrt_fp32_peak_probe",
     "rrt_camera_from", "rrt_path_count", "rrt_path_name", "rrt_path_num_keys", "rrt_path_duration",
     "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest",
+    "rrt_image_load", "rrt_image_decode", "rrt_image_free", "rrt_image_last_error", "rrt_sky_load",
     "rrt_peer_frame_create", "rrt_peer_frame_open", "rrt_peer_frame_close",
     "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
 ]
@@ -116,6 +117,12 @@ def load() -> C.CDLL:
     lib.rrt_band_rows.argtypes = [P(Band), ci]
     lib.rrt_assemble_bands.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]
     lib.rrt_read_counters.argtypes = [vp, P(Counters), ci]
+    lib.rrt_image_load.argtypes = [C.c_char_p, P(P(C.c_uint8)), P(ci), P(ci)]
+    lib.rrt_image_decode.argtypes = [vp, C.c_size_t, P(P(C.c_uint8)), P(ci), P(ci)]
+    lib.rrt_image_free.argtypes = [P(C.c_uint8)]
+    lib.rrt_image_free.restype = None
+    lib.rrt_image_last_error.restype = C.c_char_p
+    lib.rrt_sky_load.argtypes = [vp, C.c_char_p, P(vp)]
     lib.rrt_peer_frame_create.argtypes = [vp, C.c_size_t, P(vp), vp]
     lib.rrt_peer_frame_open.argtypes = [vp, vp, P(vp)]
     lib.rrt_peer_frame_close.argtypes = [vp, vp, ci]

@@ -301,6 +301,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
         }
     };
     enum : int { kRanOut = 0, kCaptured = 1, kEscaped = 2, kRedo = 3 };
+    int burst_after = 0;   // no burst before this iteration count (set when one was rejected)
     for (;;) {
         int ev = kRanOut;
         V3 q = p, v_in = v;   // pre-step state: media and the escape test use q (:68-69, :120)
@@ -312,30 +313,28 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
         // standing alone at the top of every iteration (it was ~20 % of the stall samples there).
         float r2 = rrt::norm2_loop(p);
         r = rrt::sqrt_rn_fast(r2);                                                            // :44
-#pragma unroll 1
-        while (it < max_steps) {                                                              // :41
-            if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
 #if RRT_BURST_K > 0
-            // Vacuum burst.  Most steps (94 % of the headline frame's) happen outside every step-size zone, with the
-            // whole-warp step h[0] and no medium; there the horizon test (:47), the zone logic (:54-62), the media
-            // branch (:67) and the escape test (:120) are all false.  When the radius says the next kBurst steps will stay
-            // in that regime, take them straight-line with none of those checks, tracking only the smallest radius any
-            // stage or state saw and the largest state radius (FMNMX on the ALU pipe, off the FMA pipe), and validate
-            // afterwards: min >= every threshold the checks compare against, max <= 250.  If the validation fails the
-            // state is rolled back.  Either way control falls through to the checked step below, so the result is the
-            // reference's on every path -- the entry margin only decides how often a burst is wasted, never what is
-            // computed.  The block has no break / continue on purpose: it is a structured `if`, so the lanes that took
-            // it reconverge with the others before the checked step (a `continue` here left the two groups of a warp
-            // split for the rest of their rays: 4-6 % slower on the media-heavy cameras instead of faster).
-            // Warp-uniform on purpose: the burst is taken only when EVERY lane still in the loop qualifies.  A lane that
-            // burst on its own would finish its vacuum phase in 1/kBurst of the iterations -- alone, while its tile
-            // mates are still in a zone -- instead of sharing each execution of the step with the other vacuum lanes of
-            // the warp: measured with a per-lane burst, the media-heavy cameras (mixed tiles) got 2-6 % slower, not
-            // faster.  (__activemask: the vote only decides how the steps are scheduled, never what they compute.)
-            // The vote costs the iterations that cannot burst one VOTE: the lanes in the loop are counted here, the
-            // qualifying ones inside the branch, and the burst runs when the two sets are the same.
+        // ---- phase 1: vacuum bursts ------------------------------------------------------------------------------
+        // Most steps (94 % of the headline frame's) happen outside every step-size zone, with the whole-warp step h[0]
+        // and no medium; there the horizon test (:47), the zone logic (:54-62), the media branch (:67) and the escape test
+        // (:120) are all false.  While the radii say the next kBurst steps will stay in that regime, take them straight-line
+        // with none of those checks, tracking only the smallest radius any stage or state saw and the largest state radius
+        // (FMNMX on the ALU pipe, off the FMA pipe), and validate afterwards: min >= every threshold the checks compare
+        // against, max <= 250.  If the validation fails the state is rolled back.  Either way control goes on to the
+        // checked steps of phase 2, so the result is the reference's on every path -- the entry margin only decides how
+        // often a burst is wasted, never what is computed.
+        //  * Warp-uniform on purpose: a burst is taken only when EVERY lane still in the loop qualifies.  A lane that
+        //    burst on its own would finish its vacuum phase in 1/kBurst of the iterations -- alone, while its tile mates
+        //    are still in a zone -- instead of sharing each execution of the step with the other vacuum lanes of the warp
+        //    (measured with per-lane bursts: the media-heavy cameras, whose tiles are mixed, got 2-6 % slower).
+        //    (__activemask: the vote only decides how the steps are scheduled, never what they compute.)
+        //  * A loop of its own, in front of the checked loop rather than a block inside it: the zone / media iterations
+        //    then do not jump over 3 KB of burst code every time (instruction-fetch stalls doubled on the media-heavy
+        //    C3 frame with the block inside: ncu no_instruction 0.54 -> 1.05 warps per issue).
+        {
             const unsigned in_loop = __activemask();
-            if (r >= burst_lo && r <= burst_hi && it + kBurst < max_steps && __activemask() == in_loop) {
+#pragma unroll 1
+            while (r >= burst_lo && r <= burst_hi && it >= burst_after && it + kBurst < max_steps && __activemask() == in_loop) {
                 const V3 ps = p, vs = v;
                 const float r2s = r2, rs = r;
                 float mn = r, mx = r;
@@ -352,12 +351,20 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
                         mx = fmaxf(mx, r);
                     }
                 }
-                // mn / mx include the radius of the state the checked step below starts from: its horizon test is
-                // covered too, and its own escape test will see r <= 250
-                if (mn >= burst_min && mx <= 250.0f) it += kBurst;
-                else { p = ps; v = vs; r2 = r2s; r = rs; }
+                // mn / mx include the radius of the state the next step starts from: its horizon test is covered too,
+                // and its own escape test will see r <= 250
+                if (mn >= burst_min && mx <= 250.0f) { it += kBurst; continue; }
+                p = ps; v = vs; r2 = r2s; r = rs;
+                burst_after = it + kBurst;   // a rejected burst (|v| well above 1): take the next steps one by one
+                break;
             }
+        }
 #endif
+        // ---- phase 2: checked steps, until the ray ends or the whole warp is back in the burst window ------------------
+        bool rewind = false;
+#pragma unroll 1
+        while (it < max_steps) {                                                              // :41
+            if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
             unsigned z = 0;
             float rmin;
             q = p;
@@ -407,7 +414,14 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { ev = kEscaped; break; }               // :120
             r2 = r2_next;
             r = r_next;
+#if RRT_BURST_K > 0
+            {   // one VOTE per checked step: the lanes in the loop here, the qualifying ones inside the branch
+                const unsigned in_loop = __activemask();
+                if (r >= burst_lo && r <= burst_hi && it >= burst_after && it + kBurst < max_steps && __activemask() == in_loop) { rewind = true; break; }
+            }
+#endif
         }
+        if (rewind) continue;   // back to phase 1 (p, v, it carry over; r2 / r are recomputed from p, bit for bit the same)
         if (ev == kRedo) {
             // outside the branch-free domain, or geodesics.h:33 can fire: redo this step with the general code
             const float h = C.h[zone_index];

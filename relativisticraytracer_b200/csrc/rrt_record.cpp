@@ -1,11 +1,12 @@
 // rrt_record -- headless recorder: the reference's "P then R" session (camera-path playback under the recorder's
 // fixed 1/24 s clock, src/main.cpp:171-220, 505-528) without a window, written against the C ABI only.
 //
-//   rrt_record <path 0..2> <frames> <width> <height> <target> [--spin a] [--y4m] [--sky file.rgba W H] [--device n]
+//   rrt_record <path 0..2> <frames> <width> <height> <target> [--spin a] [--y4m] [--sky file.png|file.jpg] [--sky-raw file.rgba W H] [--device n]
 //
 // <target> is a file, or "|command" (e.g. the string rrt_sink_ffmpeg_command returns) which is popen()ed like the
 // reference's recorder does.  Two frames are kept in flight (rrt_render_host_async on two streams, pinned host
-// frames); frames reach the sink in order.  Without --sky a smooth procedural RGBA8 map is used.
+// frames); frames reach the sink in order.  --sky decodes the file exactly like the reference's loadSkybox does
+// (rrt_sky_load: the bytes stb_image returns, src/main.cpp:237-266); without a sky a smooth procedural RGBA8 map is used.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -27,7 +28,7 @@
 
 int main(int argc, char** argv) {
     if (argc < 6) {
-        std::fprintf(stderr, "usage: %s <path 0..%d> <frames> <width> <height> <target> [--spin a] [--y4m] [--sky f W H] [--device n]\n",
+        std::fprintf(stderr, "usage: %s <path 0..%d> <frames> <width> <height> <target> [--spin a] [--y4m] [--sky f.png|f.jpg] [--sky-raw f.rgba W H] [--device n]\n",
                      argv[0], rrt_path_count() - 1);
         return 2;
     }
@@ -35,12 +36,14 @@ int main(int argc, char** argv) {
     const char* target = argv[5];
     float spin = 0.0f;  // SPIN_A of the reference's config.h
     int format = RRT_SINK_RGBA, device = 0, sky_w = 1024, sky_h = 512;
-    const char* sky_file = nullptr;
+    const char* sky_file = nullptr;   // headerless RGBA8
+    const char* sky_image = nullptr;  // PNG / JPEG, decoded by rrt_sky_load
     for (int i = 6; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--spin") && i + 1 < argc) spin = (float)std::atof(argv[++i]);
         else if (!std::strcmp(argv[i], "--y4m")) format = RRT_SINK_Y4M;
         else if (!std::strcmp(argv[i], "--device") && i + 1 < argc) device = std::atoi(argv[++i]);
-        else if (!std::strcmp(argv[i], "--sky") && i + 3 < argc) { sky_file = argv[i + 1]; sky_w = std::atoi(argv[i + 2]); sky_h = std::atoi(argv[i + 3]); i += 3; }
+        else if (!std::strcmp(argv[i], "--sky") && i + 1 < argc) sky_image = argv[++i];
+        else if (!std::strcmp(argv[i], "--sky-raw") && i + 3 < argc) { sky_file = argv[i + 1]; sky_w = std::atoi(argv[i + 2]); sky_h = std::atoi(argv[i + 3]); i += 3; }
         else { std::fprintf(stderr, "unknown option %s\n", argv[i]); return 2; }
     }
     if (path < 0 || path >= rrt_path_count() || frames <= 0 || w <= 0 || h <= 0 || sky_w <= 0 || sky_h <= 0) return 2;
@@ -50,8 +53,14 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "rrt_context_create: %d (%s)\n", rc, rrt_last_error(nullptr));
         return 1;
     }
-    std::vector<uint8_t> sky_px((size_t)sky_w * sky_h * 4);
-    if (sky_file) {
+    rrt_sky* sky = nullptr;
+    std::vector<uint8_t> sky_px(sky_image ? 0 : (size_t)sky_w * sky_h * 4);
+    if (sky_image) {
+        if (int rc = rrt_sky_load(ctx, sky_image, &sky)) {
+            std::fprintf(stderr, "rrt_sky_load(%s): %d (%s)\n", sky_image, rc, rc == RRT_ERR_CUDA ? rrt_last_error(ctx) : rrt_image_last_error());
+            return 1;
+        }
+    } else if (sky_file) {
         FILE* f = std::fopen(sky_file, "rb");
         if (!f || std::fread(sky_px.data(), 1, sky_px.size(), f) != sky_px.size()) { std::fprintf(stderr, "cannot read %s\n", sky_file); return 1; }
         std::fclose(f);
@@ -66,8 +75,7 @@ int main(int argc, char** argv) {
                 p[3] = 255;
             }
     }
-    rrt_sky* sky = nullptr;
-    CHECK(rrt_sky_create(ctx, sky_px.data(), sky_w, sky_h, &sky));
+    if (!sky) CHECK(rrt_sky_create(ctx, sky_px.data(), sky_w, sky_h, &sky));
     rrt_params prm;
     rrt_default_params(&prm);
     prm.spin_a = spin;

@@ -38,21 +38,39 @@ def procedural_sky(width: int = 4096, height: int = 2048, seed: int = 1234, star
     return out
 
 
+def decode_image(path: str) -> np.ndarray:
+    """rrt_image_load (C ABI, csrc/rrt_image.cpp): PNG / baseline JPEG -> the RGBA8 array stb_image returns for
+    ``stbi_load(path, &w, &h, &c, 4)``, byte for byte.  Raises RrtError for files outside the decoder's subset."""
+    import ctypes as C
+    from . import _capi
+    lib = _capi.load()
+    px, w, h = C.POINTER(C.c_uint8)(), C.c_int(), C.c_int()
+    rc = lib.rrt_image_load(path.encode(), C.byref(px), C.byref(w), C.byref(h))
+    if rc != _capi.OK:
+        raise _capi.RrtError(rc, f"{path}: {lib.rrt_image_last_error().decode()}")
+    try:
+        return np.ctypeslib.as_array(px, shape=(h.value, w.value, 4)).copy()
+    finally:
+        lib.rrt_image_free(px)
+
+
 def load_skybox(path: str, width: int | None = None, height: int | None = None) -> np.ndarray:
     """Host half of the reference's ``loadSkybox`` (src/main.cpp:237-245): decode an equirectangular image file
     into the RGBA8, rows-top-down array ``stbi_load(path, &w, &h, &c, 4)`` returns, ready for
     ``Renderer.create_sky`` (the device half, src/main.cpp:246-263).
 
-    * ``.png`` / ``.jpg`` / anything PIL opens: decoded with PIL.  PNG decoding is lossless, so the bytes equal
-      stb_image's.  JPEG decoders are allowed to differ in their IDCT / chroma upsampling: PIL (libjpeg) and
-      stb_image v2.30 give slightly different bytes for ``skybox2.jpg``; for byte-level
-      parity with a reference build on a JPEG asset, decode once with the reference's decoder and ship ``.npy``.
+    * ``.png`` / ``.jpg`` / ``.jpeg``: the library's own decoder (``decode_image`` -> ``rrt_image_load``), whose output
+      equals stb_image v2.30's byte for byte -- including for JPEG, where decoders are free to differ (PIL / libjpeg
+      do not reproduce stb_image's bytes for the reference's ``skybox2.jpg``).  Files outside its subset (progressive
+      JPEG, 16-bit / interlaced PNG) raise instead of being decoded differently from the reference.
     * ``.npy``: an array saved with ``numpy.save`` ([h, w, 3] or [h, w, 4] uint8).
     * ``.rgba`` / ``.raw``: headerless RGBA8, ``width`` and ``height`` required.
 
     Grey and grey+alpha sources are expanded the way stb_image does for ``req_comp = 4`` (grey replicated to
     RGB, missing alpha = 255)."""
     ext = path.rsplit(".", 1)[-1].lower() if "." in path else ""
+    if ext in ("png", "jpg", "jpeg"):
+        return decode_image(path)
     if ext == "npy":
         img = np.load(path)
     elif ext in ("rgba", "raw"):
@@ -63,11 +81,7 @@ def load_skybox(path: str, width: int | None = None, height: int | None = None) 
             raise ValueError(f"{path}: expected {width * height * 4} bytes, found {img.size}")
         img = img.reshape(height, width, 4)
     else:
-        from PIL import Image
-        with Image.open(path) as im:
-            if im.mode not in ("RGB", "RGBA", "L", "LA"):
-                im = im.convert("RGBA")
-            img = np.asarray(im)
+        raise ValueError(f"{path}: unsupported skybox format (png, jpg, npy, rgba)")
     img = np.asarray(img)
     if img.dtype != np.uint8:
         raise ValueError("skybox must be 8 bits per channel")

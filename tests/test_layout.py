@@ -17,7 +17,8 @@ def test_product_never_touches_the_oracle():
 
 
 def test_oracle_says_it_is_test_infrastructure():
-    for f in ("oracle_abi.h", "rrt_oracle.c", "ref_harness.cpp", "tex_emul.h", "__init__.py", "ref_cuda_harness.cu"):
+    for f in ("oracle_abi.h", "rrt_oracle.c", "ref_harness.cpp", "tex_emul.h", "__init__.py", "ref_cuda_harness.cu",
+              "ref_cuda_planes.cu", "ref_cuda_planes_prelude.h", "ref_stb.c"):
         assert "TEST INFRASTRUCTURE ONLY" in open(os.path.join(ROOT, "oracle", f)).read(), f
 
 
