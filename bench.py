@@ -400,7 +400,7 @@ def main():
                 launches += 1
                 dist.all_reduce(bf.token)                                               # every band has landed
                 if to_host and rank == 0:
-                    host_frame.copy_(bf.frame, non_blocking=True)
+                    bf.peer.read_into(host_frame)
             else:
                 r.render(prm, cam, fx, sky, TIME, w, h, band=bf.band, out=bf.packed, layout=rrt.OUT_PACKED)
                 e1.record(stream)

@@ -204,6 +204,9 @@ int rrt_assemble_bands(rrt_context* ctx, const void* d_packed, int rows_per_rank
 #define RRT_PEER_HANDLE_BYTES 64
 int rrt_peer_frame_create(rrt_context* ctx, size_t bytes, void** d_frame, uint8_t handle[RRT_PEER_HANDLE_BYTES]);
 int rrt_peer_frame_open(rrt_context* ctx, const uint8_t handle[RRT_PEER_HANDLE_BYTES], void** d_frame);
+/* Stream-ordered copy of a peer frame (or any device buffer) to `dst`, which may be pinned host memory or device
+ * memory (cudaMemcpyDefault): how rank 0 hands the assembled frame on without wrapping the raw allocation. */
+int rrt_peer_frame_read(rrt_context* ctx, const void* d_frame, size_t bytes, void* dst, void* stream);
 /* owner != 0: the creating process frees the frame; owner == 0: a mapping process unmaps it */
 int rrt_peer_frame_close(rrt_context* ctx, void* d_frame, int owner);
 

@@ -76,7 +76,7 @@ SYMBOLS = [
     "rrt_camera_from", "rrt_path_count", "rrt_path_name", "rrt_path_num_keys", "rrt_path_duration",
     "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest",
     "rrt_image_load", "rrt_image_decode", "rrt_image_free", "rrt_image_last_error", "rrt_sky_load",
-    "rrt_peer_frame_create", "rrt_peer_frame_open", "rrt_peer_frame_close",
+    "rrt_peer_frame_create", "rrt_peer_frame_open", "rrt_peer_frame_read", "rrt_peer_frame_close",
     "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
 ]
 
@@ -125,6 +125,7 @@ def load() -> C.CDLL:
     lib.rrt_sky_load.argtypes = [vp, C.c_char_p, P(vp)]
     lib.rrt_peer_frame_create.argtypes = [vp, C.c_size_t, P(vp), vp]
     lib.rrt_peer_frame_open.argtypes = [vp, vp, P(vp)]
+    lib.rrt_peer_frame_read.argtypes = [vp, vp, C.c_size_t, vp, vp]
     lib.rrt_peer_frame_close.argtypes = [vp, vp, ci]
     lib.rrt_geodesic_acc_batch.argtypes = [vp, P(Params), ci, vp, vp, vp]
     lib.rrt_rk4_step_batch.argtypes = [vp, P(Params), ci, vp, vp, vp]

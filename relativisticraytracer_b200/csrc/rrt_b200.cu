@@ -515,6 +515,14 @@ int rrt_peer_frame_open(rrt_context* ctx, const uint8_t handle[RRT_PEER_HANDLE_B
     return RRT_OK;
 }
 
+int rrt_peer_frame_read(rrt_context* ctx, const void* d_frame, size_t bytes, void* dst, void* stream) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!d_frame || !dst || bytes == 0) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_peer_frame_read: bad argument");
+    DevGuard g(ctx->device);
+    RRT_CU(ctx, cudaMemcpyAsync(dst, d_frame, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return RRT_OK;
+}
+
 int rrt_peer_frame_close(rrt_context* ctx, void* d_frame, int owner) {
     if (!ctx) return RRT_ERR_BAD_ARG;
     if (!d_frame) return RRT_OK;

@@ -87,7 +87,7 @@ PLANE_SPECS = {"hdr": (4, torch.float32), "dir": (4, torch.float32), "emis": (4,
 class PeerFrame:
     """A device frame on the encoding GPU that other processes' render kernels store into directly (C ABI
     rrt_peer_frame_*; CUDA IPC).  The owner (rank 0) creates it and passes ``handle`` (64 bytes) to the other ranks,
-    which ``open`` it; ``tensor`` (owner only) is a torch view [h, w, 4] uint8 of the same memory."""
+    which ``open`` it; the owner reads the assembled frame out with ``read_into`` (pinned host or device tensor)."""
 
     def __init__(self, renderer: "Renderer", h: int, w: int, handle: Optional[bytes] = None):
         self.r, self.h, self.w, self.nbytes = renderer, h, w, h * w * 4
@@ -103,14 +103,16 @@ class PeerFrame:
             buf = (C.c_uint8 * 64).from_buffer_copy(self.handle)
             renderer._check(renderer._lib.rrt_peer_frame_open(renderer._ctx, buf, C.byref(ptr)))
         self.ptr = int(ptr.value)
-        self.tensor = None
-        if self.owner:
-            self.__cuda_array_interface__ = {"shape": (h, w, 4), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
-            self.tensor = torch.as_tensor(self, device=torch.device("cuda", renderer.device))
+
+    def read_into(self, dst: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Stream-ordered copy of the frame into `dst` (pinned host or device uint8 tensor of the frame's size)."""
+        assert dst.dtype == torch.uint8 and dst.is_contiguous() and dst.numel() == self.nbytes
+        st = stream if stream is not None else torch.cuda.current_stream(self.r.device)
+        self.r._check(self.r._lib.rrt_peer_frame_read(self.r._ctx, C.c_void_p(self.ptr), C.c_size_t(self.nbytes),
+                                                      C.c_void_p(dst.data_ptr()), C.c_void_p(st.cuda_stream)))
 
     def close(self):
         if self.ptr:
-            self.tensor = None
             self.r._lib.rrt_peer_frame_close(self.r._ctx, C.c_void_p(self.ptr), 1 if self.owner else 0)
             self.ptr = 0
 

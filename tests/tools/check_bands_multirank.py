@@ -34,7 +34,15 @@ for exchange in ("peer", "nccl"):
         torch.cuda.synchronize()
         dist.barrier()
         if rank == 0:
-            assert torch.equal(bf.frame, want[i]), f"BandedFrame {exchange} camera {i}"
+            if not torch.equal(bf.frame, want[i]):      # say where, before failing
+                bad = (bf.frame != want[i]).any(dim=2).any(dim=1).nonzero().flatten().tolist()
+                msg = f"BandedFrame {exchange} camera {i}: {len(bad)} rows differ, first {bad[:6]}, frame sum {int(bf.frame.sum())}"
+                if bf.peer is not None:
+                    chk = torch.zeros_like(want[i])
+                    bf.peer.read_into(chk)
+                    torch.cuda.synchronize()
+                    msg += f"; explicit copy of the peer frame equal to expected: {bool(torch.equal(chk, want[i]))}"
+                raise AssertionError(msg)
     for to_host in (False, True):
         pipe = FramePipeline(r, W, H, 8, depth=3, to_host=to_host, exchange=exchange)
         assert pipe.exchange == exchange
