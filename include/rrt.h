@@ -279,6 +279,15 @@ int rrt_fp32_peak_probe(rrt_context* ctx, int iters, double* tflops, double* ms)
 int rrt_exact_math_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_t* div_mismatches,
                             uint64_t* sqrt_mismatches);
 
+/* Profiling aid: while d_log is non-NULL every render launch of this context writes, per 8x4-pixel tile (index =
+ * the tile's ticket, tiles beyond `entries` are skipped), four uint64: %globaltimer at the start and at the end of the
+ * tile (ns), (tile_row << 32 | tile_col), (sm_id << 32 | steps of the tile's longest ray).  d_log is a caller-owned device
+ * buffer of entries * 32 bytes; pass NULL to switch the log off.  Only libraries built with -DRRT_WITH_TILE_LOG
+ * (`make -C csrc timeline` -> build/timeline/librrt_b200_timeline.so) carry the instrumentation -- its extra live values
+ * cost the step loop ~3 % through register allocation, so the product library returns RRT_ERR_UNSUPPORTED for a non-NULL
+ * log.  Used by tools/tile_timeline.py to see what a launch's tail consists of. */
+int rrt_debug_tile_log(rrt_context* ctx, void* d_log, size_t entries);
+
 /* Rounding contract of the probes that take no rrt_params (hash31 / noise3D / fbm): 1 the RRT_FLAG_FMAD contract
  * (default, like rrt_default_params), 0 strict.  The other probes and rrt_render follow rrt_params.flags. */
 int rrt_set_probe_contract(rrt_context* ctx, int fmad);

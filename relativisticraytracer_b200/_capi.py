@@ -77,7 +77,7 @@ SYMBOLS = [
     "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest",
     "rrt_image_load", "rrt_image_decode", "rrt_image_free", "rrt_image_last_error", "rrt_sky_load",
     "rrt_peer_frame_create", "rrt_peer_frame_open", "rrt_peer_frame_read", "rrt_peer_frame_close",
-    "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
+    "rrt_debug_tile_log", "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
 ]
 
 _lib = None
@@ -151,6 +151,7 @@ def load() -> C.CDLL:
     lib.rrt_path_state.argtypes = [ci, cf, P(Camera), vp]
     lib.rrt_path_clock.argtypes = [ci, cf]
     lib.rrt_path_clock.restype = cf
+    lib.rrt_debug_tile_log.argtypes = [vp, vp, C.c_size_t]
     lib.rrt_set_probe_contract.argtypes = [vp, ci]
     lib.rrt_set_frames_in_flight.argtypes = [vp, ci]
     lib.rrt_sink_open.argtypes = [C.c_char_p, ci, ci, ci, ci, P(vp)]

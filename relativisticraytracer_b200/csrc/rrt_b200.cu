@@ -106,6 +106,9 @@ struct rrt_context {
     unsigned long long* d_counters = nullptr;
     unsigned int* d_tickets = nullptr;
     unsigned ticket_next = 0;
+    // which FMAD render kernel: 0 auto (packed f32x2, two rays per thread, for launches without a medium; the scalar kernel
+    // otherwise -- measured, profiles/r2_history.md), 1 always scalar, 2 always packed.  RRT_KERNEL=auto|scalar|packed.
+    int kernel_choice = 0;
     int kernel_variant = 1;  // 1 tile-per-warp (the product); 2 / 3 only in -DRRT_WITH_VARIANTS builds (RRT_KERNEL_VARIANT)
     // launch configuration of every render kernel seen so far (resident CTAs per SM, carve-out applied): queried once
     struct LaunchCfg { const void* kern; int per_sm; };
@@ -113,6 +116,8 @@ struct rrt_context {
     int n_launch_cfg = 0;
     void* d_frame[RRT_HOST_SLOTS] = {};  // device frames behind the host-destination calls, one per slot
     size_t d_frame_bytes[RRT_HOST_SLOTS] = {};
+    unsigned long long* tile_log = nullptr;   // rrt_debug_tile_log: caller-owned device buffer, or null
+    unsigned tile_log_cap = 0;
     bool probe_fmad = true;   // contract of the parameter-less probes (hash31 / noise3D / fbm): like rrt_default_params
     int frames_in_flight = 1; // render launches expected to run concurrently: each gets 1/n of the resident-CTA slots
     std::string err;
@@ -244,6 +249,7 @@ int rrt_context_create(int device, rrt_context** out) {
     if (!ctx) return fail(nullptr, RRT_ERR_NOMEM, "out of host memory");
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* k = std::getenv("RRT_KERNEL")) ctx->kernel_choice = !std::strcmp(k, "packed") ? 2 : (!std::strcmp(k, "scalar") ? 1 : 0);
 #ifdef RRT_WITH_VARIANTS
     if (const char* kv = std::getenv("RRT_KERNEL_VARIANT")) {
         const int k = std::atoi(kv);
@@ -395,6 +401,8 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     if (planes) A.planes = *planes;
     A.sky = (cudaTextureObject_t)sky_texture;
     A.counters = ctx->d_counters;
+    A.tile_log = ctx->tile_log;
+    A.tile_log_cap = ctx->tile_log_cap;
     A.ticket = ctx->d_tickets + (ctx->ticket_next++ % kTicketRing);
     RRT_CU(ctx, cudaMemsetAsync(A.ticket, 0, sizeof(unsigned), st));
 
@@ -404,6 +412,11 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     const rrtk::KernelSet* ks = fmad ? rrtk::rrt_kernels_fmad() : rrtk::rrt_kernels_strict();
     void (*kern)(const FrameArgs) = ks->render[spin ? 1 : 0][media ? 1 : 0];
     int variant = 1;
+    long long rays_per_block = kRenderBlock;
+    if (ks->render_packed[0][0] && (ctx->kernel_choice == 2 || (ctx->kernel_choice == 0 && !media))) {
+        kern = ks->render_packed[spin ? 1 : 0][media ? 1 : 0];
+        rays_per_block = 64;
+    }
 #ifdef RRT_WITH_VARIANTS
     // measured alternatives (strict arithmetic only): 2 two rays per thread (f32x2), 3 wavefront in a warp
     variant = fmad ? 1 : ctx->kernel_variant;
@@ -427,7 +440,7 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
         if (per_sm < 1) per_sm = 1;
         if (ctx->n_launch_cfg < 16) ctx->launch_cfg[ctx->n_launch_cfg++] = {(const void*)kern, per_sm};
     }
-    const long long rays_per_block = (variant == 2 ? 2 : 1) * (long long)block;
+    if (variant != 1) rays_per_block = (variant == 2 ? 2 : 1) * (long long)block;
     // A persistent launch normally fills every resident-CTA slot.  When the caller keeps n frames in flight, each
     // launch takes 1/n of the slots so that the n kernels run side by side from the start: a launch then lasts
     // n times longer than its critical path (one tile of disk-plane rays, ~17 ms at 4K) needs, instead of ending
@@ -657,6 +670,18 @@ int rrt_set_frames_in_flight(rrt_context* ctx, int n) {
     if (!ctx) return RRT_ERR_BAD_ARG;
     if (n < 1 || n > RRT_HOST_SLOTS) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_set_frames_in_flight: n out of range");
     ctx->frames_in_flight = n;
+    return RRT_OK;
+}
+
+int rrt_debug_tile_log(rrt_context* ctx, void* d_log, size_t entries) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+#ifndef RRT_WITH_TILE_LOG
+    if (d_log) return fail(ctx, RRT_ERR_UNSUPPORTED, "rrt_debug_tile_log: this library was built without -DRRT_WITH_TILE_LOG (make -C csrc timeline)");
+#endif
+    if (entries > 0xffffffffull) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_debug_tile_log: too many entries");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->tile_log = d_log ? (unsigned long long*)d_log : nullptr;
+    ctx->tile_log_cap = d_log ? (unsigned)entries : 0u;
     return RRT_OK;
 }
 

@@ -27,11 +27,14 @@ struct FrameArgs {
     cudaTextureObject_t sky;
     unsigned long long* counters;  // rrt_counters, 8 x u64
     unsigned int* ticket;          // tile ticket for this launch
+    unsigned long long* tile_log;  // optional profiling aid (rrt_debug_tile_log): 4 x u64 per tile, see render_kernel
+    unsigned int tile_log_cap;     // entries the log can hold
 };
 
 // kernels of one rounding contract
 struct KernelSet {
     void (*render[2][2])(const FrameArgs);  // [spin != 0][media]
+    void (*render_packed[2][2])(const FrameArgs);  // two rays per thread in f32x2 registers (rrt_packed.cuh); FMAD contract only
     void (*acc)(Consts, int, const float*, const float*, float*);
     void (*rk4)(Consts, int, float*, float*, const float*);
     void (*euler)(Consts, int, float*, float*, const float*);
@@ -478,6 +481,10 @@ __global__ void __launch_bounds__(kRenderBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : R
         const int y = (grp * A.band_nranks + A.band_rank) * A.band_group + (ly - grp * A.band_group);
         if (y >= A.h) continue;
 
+#ifdef RRT_WITH_TILE_LOG
+        unsigned long long t_begin = 0;
+        if (A.tile_log) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
         RayResult R;
         trace_ray<SPIN, MEDIA>(A, x, y, R);
 
@@ -486,6 +493,19 @@ __global__ void __launch_bounds__(kRenderBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : R
         c_steps += (unsigned)R.steps;
         c_disk += R.n_disk; c_dust += R.n_dust; c_dense += R.n_dense;
         c_cap += R.captured; c_exh += R.exhausted; c_esc += (!R.captured && !R.exhausted); c_touch += R.touched;
+#ifdef RRT_WITH_TILE_LOG   // (a build option, not a run-time one: the extra live values cost the step loop ~3 % through register allocation)
+        if (A.tile_log) {   // who traced which tile from when to when (ns, %globaltimer) and how many steps its slowest ray took
+            const int most = __reduce_max_sync(__activemask(), R.steps);
+            if (lane == __ffs(__activemask()) - 1 && tile < A.tile_log_cap) {
+                unsigned long long t_end;
+                unsigned smid;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                unsigned long long* e = A.tile_log + 4ull * tile;
+                e[0] = t_begin; e[1] = t_end; e[2] = ((unsigned long long)ty << 32) | (unsigned)tx; e[3] = ((unsigned long long)smid << 32) | (unsigned)most;
+            }
+        }
+#endif
     }
 
     // one set of atomics per warp
@@ -573,8 +593,18 @@ __global__ void k_sky(cudaTextureObject_t sky, int n, const float* tx, const flo
     if (i < n) out[i] = tex2D<float4>(sky, tx[i], ty[i]);
 }
 
+}  // namespace
+#if RRT_FMAD
+#include "rrt_packed.cuh"
+#endif
+namespace {
 const rrtk::KernelSet kKernelSet = {
     {{render_kernel<false, false>, render_kernel<false, true>}, {render_kernel<true, false>, render_kernel<true, true>}},
+#if RRT_FMAD
+    {{render_kernel_p<false, false>, render_kernel_p<false, true>}, {render_kernel_p<true, false>, render_kernel_p<true, true>}},
+#else
+    {{nullptr, nullptr}, {nullptr, nullptr}},
+#endif
     k_acc, k_rk4, k_euler, k_redshift, k_hash31, k_noise3d, k_fbm, k_disk_temp, k_disk_density, k_dust_density,
 };
 }  // namespace

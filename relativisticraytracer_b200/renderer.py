@@ -240,6 +240,15 @@ class Renderer:
         """rrt_set_frames_in_flight: each launch takes 1/n of the resident-CTA slots (n concurrent frames)."""
         self._check(self._lib.rrt_set_frames_in_flight(self._ctx, int(n)))
 
+    def tile_log(self, log: Optional[torch.Tensor]) -> None:
+        """rrt_debug_tile_log: per-tile (start ns, end ns, row<<32|col, sm<<32|max steps) into `log` ([n, 4] int64/uint64
+        device tensor), or None to switch it off."""
+        if log is None:
+            self._check(self._lib.rrt_debug_tile_log(self._ctx, None, 0))
+        else:
+            assert log.is_cuda and log.is_contiguous() and log.element_size() == 8 and log.shape[-1] == 4
+            self._check(self._lib.rrt_debug_tile_log(self._ctx, C.c_void_p(log.data_ptr()), C.c_size_t(log.shape[0])))
+
     def set_probe_contract(self, fmad: bool) -> None:
         """Rounding contract of hash31 / noise3d / fbm (the probes without a parameter block)."""
         self._check(self._lib.rrt_set_probe_contract(self._ctx, 1 if fmad else 0))
