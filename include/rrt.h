@@ -288,6 +288,13 @@ int rrt_exact_math_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_
  * log.  Used by tools/tile_timeline.py to see what a launch's tail consists of. */
 int rrt_debug_tile_log(rrt_context* ctx, void* d_log, size_t entries);
 
+/* Self-test of the media code's split powf (include/rrt_device.cuh: pow_log2 + pow_exp2, libdevice's own algorithm cut
+ * where the exponent enters so that one log2 serves several powers of the same base) against libdevice's powf on `n`
+ * pseudo-random positive normal bases, with the exponents the media code uses and with random exponents.  Outputs the
+ * number of results that differ in any bit (expected: 0 and 0). */
+int rrt_exact_pow_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_t* used_exponent_mismatches,
+                           uint64_t* random_exponent_mismatches);
+
 /* Rounding contract of the probes that take no rrt_params (hash31 / noise3D / fbm): 1 the RRT_FLAG_FMAD contract
  * (default, like rrt_default_params), 0 strict.  The other probes and rrt_render follow rrt_params.flags. */
 int rrt_set_probe_contract(rrt_context* ctx, int fmad);

@@ -74,7 +74,7 @@ SYMBOLS = [
     "rrt_hash31_batch", "rrt_noise3d_batch", "rrt_fbm_batch", "rrt_disk_temperature_batch",
     "rrt_disk_density_batch", "rrt_dust_density_batch", "rrt_sky_sample_batch", "rrt_fp32_peak_probe",
     "rrt_camera_from", "rrt_path_count", "rrt_path_name", "rrt_path_num_keys", "rrt_path_duration",
-    "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest",
+    "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest", "rrt_exact_pow_selftest",
     "rrt_image_load", "rrt_image_decode", "rrt_image_free", "rrt_image_last_error", "rrt_sky_load",
     "rrt_peer_frame_create", "rrt_peer_frame_open", "rrt_peer_frame_read", "rrt_peer_frame_close",
     "rrt_debug_tile_log", "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
@@ -140,6 +140,7 @@ def load() -> C.CDLL:
     lib.rrt_sky_sample_batch.argtypes = [vp, C.c_uint64, ci, vp, vp, vp]
     lib.rrt_fp32_peak_probe.argtypes = [vp, ci, P(C.c_double), P(C.c_double)]
     lib.rrt_exact_math_selftest.argtypes = [vp, C.c_uint64, C.c_uint64, P(C.c_uint64), P(C.c_uint64)]
+    lib.rrt_exact_pow_selftest.argtypes = [vp, C.c_uint64, C.c_uint64, P(C.c_uint64), P(C.c_uint64)]
     lib.rrt_camera_from.argtypes = [P(C.c_float * 3), cf, cf, P(Camera)]
     lib.rrt_camera_from.restype = None
     lib.rrt_path_count.restype = ci

@@ -79,6 +79,29 @@ __global__ void k_exact_math(unsigned long long seed, unsigned long long n, unsi
     if (bad_sqrt) atomicAdd(bad + 1, bad_sqrt);
 }
 
+// pow_exp2(pow_log2(x), y) (include/rrt_device.cuh) vs libdevice's powf on random positive normal bases: the exponents the
+// media code uses, and random ones.
+__global__ void k_exact_pow(unsigned long long seed, unsigned long long n, unsigned long long* bad) {
+    const float ys[8] = {0.5f, 0.4f, 1.5f, 1.6f, -0.75f, 4.0f, 1.2f, 0.2f};
+    unsigned long long bad_used = 0, bad_rand = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long a = mix64(seed + 2 * i), b = mix64(seed + 2 * i + 1);
+        // base: half of the draws in the media code's range 2^[-8, 8], half in 2^[-60, 60]
+        const int ex = (a >> 40) & 1 ? (int)((a >> 23) % 17) - 8 : (int)((a >> 23) % 121) - 60;
+        const float x = make_float((unsigned)a, ex, false);
+        const float y_used = ys[(b >> 50) & 7];
+        const float y_rand = __uint_as_float((unsigned)b & 0x007fffffu | 0x3f800000u) * (float)((int)((b >> 30) % 9) - 3) * 0.73f + 0.011f;
+        const rrt::PowLog L = rrt::pow_log2(x);
+        const float g0 = rrt::pow_exp2(L, y_used), w0 = powf(x, y_used);
+        const float g1 = rrt::pow_exp2(L, y_rand), w1 = powf(x, y_rand);
+        if (__float_as_uint(g0) != __float_as_uint(w0)) ++bad_used;
+        if (__float_as_uint(g1) != __float_as_uint(w1) && !(g1 != g1 && w1 != w1)) ++bad_rand;
+    }
+    if (bad_used) atomicAdd(bad + 0, bad_used);
+    if (bad_rand) atomicAdd(bad + 1, bad_rand);
+}
+
 // FP32 roofline probe: 8 independent FFMA chains per thread, all operands in registers.
 __global__ void __launch_bounds__(256) k_fp32_peak(int iters, float seed, float* sink) {
     float a0 = seed, a1 = seed + 1.f, a2 = seed + 2.f, a3 = seed + 3.f, a4 = seed + 4.f, a5 = seed + 5.f, a6 = seed + 6.f,
@@ -705,6 +728,23 @@ int rrt_exact_math_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_
     RRT_CU(ctx, cudaMemcpy(h, bad.p, sizeof(h), cudaMemcpyDeviceToHost));
     *div_mismatches = h[0];
     *sqrt_mismatches = h[1];
+    return RRT_OK;
+}
+
+int rrt_exact_pow_selftest(rrt_context* ctx, uint64_t seed, uint64_t n, uint64_t* used_exponent_mismatches, uint64_t* random_exponent_mismatches) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!used_exponent_mismatches || !random_exponent_mismatches) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_exact_pow_selftest: bad argument");
+    DevGuard g(ctx->device);
+    DBuf bad;
+    RRT_CU(ctx, bad.alloc(2 * sizeof(unsigned long long)));
+    RRT_CU(ctx, cudaMemset(bad.p, 0, 2 * sizeof(unsigned long long)));
+    k_exact_pow<<<ctx->sm_count * 16, 256>>>((unsigned long long)seed, (unsigned long long)n, (unsigned long long*)bad.p);
+    RRT_CU(ctx, cudaGetLastError());
+    RRT_CU(ctx, cudaDeviceSynchronize());
+    unsigned long long h[2] = {0, 0};
+    RRT_CU(ctx, cudaMemcpy(h, bad.p, sizeof(h), cudaMemcpyDeviceToHost));
+    *used_exponent_mismatches = h[0];
+    *random_exponent_mismatches = h[1];
     return RRT_OK;
 }
 

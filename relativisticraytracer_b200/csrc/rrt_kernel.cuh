@@ -132,16 +132,17 @@ __device__ __noinline__ MediaOut media_final(const Consts& C, V3 q, V3 v, float 
         const float g = rrt::redshift(C, q, v);  // same arguments in both branches (:77, :92)
         if (dd > 0.001f) {                                                                // :76-88
             float Tk = rrt::disk_temperature(C, r);
-            float tn = rrt::t_powf(Tk / C.disk_temp_ref, 0.5f);
-            float bol = rrt::t_powf(g, 4.0f) * tn * dd * C.disk_luminosity;
-            float ct = g * rrt::t_powf(Tk / C.disk_temp_ref, 0.4f) * 2.5f;
+            const rrt::PowBase TB = rrt::pow_base(Tk / C.disk_temp_ref);   // raised to 0.5 and to 0.4 (:79, :82)
+            float tn = rrt::pow_of(TB, 0.5f);
+            float bol = rrt::m_powf(g, 4.0f) * tn * dd * C.disk_luminosity;
+            float ct = g * rrt::pow_of(TB, 0.4f) * 2.5f;
             er += 1.0f * bol;
             eg += fminf(0.25f, 0.12f * ct) * bol;
             eb += fmaxf(0.0f, 0.01f * (ct - 2.0f)) * bol;
             kappa += dd * C.disk_opacity;
         }
         if (dc > 0.001f) {                                                                // :91-105
-            float light = 0.5f + 3.0f * rrt::t_powf(C.isco / fmaxf(r, C.isco), 1.2f);
+            float light = 0.5f + 3.0f * rrt::m_powf(C.isco / fmaxf(r, C.isco), 1.2f);
             float J = dc * C.cloud_luminosity * light;
             float sh = rrt::sstep(0.7f, 1.3f, g);
             er += 0.60f * J * rrt::mixf(1.2f, 0.8f, sh);

@@ -28,29 +28,16 @@ using rrt::Consts;
 using rrt::V3;
 using rrt::mk;
 
-typedef unsigned long long F2;   // .lo = ray A, .hi = ray B
-
-__device__ __forceinline__ F2 pk(float lo, float hi) {
-    F2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk(F2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+using rrt::f2::F2;   // .lo = ray A, .hi = ray B
+using rrt::f2::pk;
+using rrt::f2::upk;
+using rrt::f2::bc;
+using rrt::f2::neg2;
+using rrt::f2::add2;
+using rrt::f2::mul2;
+using rrt::f2::fma2;
+using rrt::f2::mul2_unfusable;
 __device__ __forceinline__ float half_of(F2 a, int hf) { float l, h; upk(a, l, h); return hf ? h : l; }
-__device__ __forceinline__ F2 bc(float c) { return pk(c, c); }
-// negation of both halves: ptxas folds it into the consumer's operand modifier (-R.F32x2)
-__device__ __forceinline__ F2 neg2(F2 a) { float l, h; upk(a, l, h); return pk(-l, -h); }
-__device__ __forceinline__ F2 add2(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ F2 mul2(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// A rounded product that is then ADDED (not fused): ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
-// (it does not do that to the scalar .rn forms), so the product is formed by two scalar multiplies.
-__device__ __forceinline__ F2 mul2_unfusable(F2 a, F2 b) {
-    float al, ah, bl, bh;
-    upk(a, al, ah);
-    upk(b, bl, bh);
-    return pk(__fmul_rn(al, bl), __fmul_rn(ah, bh));
-}
 
 struct V3x2 {
     F2 x, y, z;

@@ -259,6 +259,12 @@ class Renderer:
         self._check(self._lib.rrt_exact_math_selftest(self._ctx, C.c_uint64(seed), C.c_uint64(n), C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def exact_pow_selftest(self, seed: int = 1, n: int = 1 << 30):
+        """rrt_exact_pow_selftest: (mismatches with the media code's exponents, mismatches with random exponents)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.rrt_exact_pow_selftest(self._ctx, C.c_uint64(seed), C.c_uint64(n), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     # ---- function-level probes (host numpy in / out) --------------------------------------------------
     @staticmethod
     def _f32(a):
