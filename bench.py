@@ -491,8 +491,11 @@ def main():
     # ---- single-frame latency and the kernel's own duration (each frame alone, bracketed) ----------------
     lat_ms, kern_ms, _ = timed(args.steps, False)
     # ---- timed region: K frames, device-resident, `depth` in flight -------------------------------------
+    l0 = r.kernel_launches()
     with ClockSampler(dev) as clk:
-        tot_ms, _, launches = timed_sequence(pipe_dev, share, args.steps)
+        tot_ms, _, _ = timed_sequence(pipe_dev, share, args.steps)
+    launches = r.kernel_launches() - l0          # kernels rank 0's context launched in the timed region (C-ABI counter)
+    split = r.split_stats()
     # ---- timed region: end to end (HOST destination, device->host copy inside) --------------------------
     timed_sequence(pipe_host, share, min(2, args.steps))
     _, e2e_ms, _ = timed_sequence(pipe_host, share, args.steps)
@@ -539,7 +542,10 @@ def main():
         "traffic": traffic["bytes"], "traffic_source": traffic["source"],
         "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
         "peak_theoretical": FP32_THEORETICAL_TFLOPS, "frac_of_theoretical": achieved_tflops / FP32_THEORETICAL_TFLOPS,
-        "flop_per_step": FLOP_PER_STEP, "kernel": "render_kernel<spin,media>", "kernel_ms": kern_ms_per_step,
+        "flop_per_step": FLOP_PER_STEP,
+        "kernel": ("trace_kernel<spin> + media_kernel + fold_kernel (+ empty sweep_kernel): the launches of one frame, timed together"
+                   if split["passes_enqueued"] else "render_kernel<spin,media>"),
+        "kernel_ms": kern_ms_per_step,
         "note": "geodesic-step FLOPs only; disk/dust density evaluations (1.1k/4.1k FLOP each) are not credited",
     }
 
@@ -567,6 +573,10 @@ def main():
                          ("rrt_render per rank storing into rank 0's peer-mapped frame + 4-byte all-reduce + D2H to pinned host" if xchg == "peer"
                           else "rrt_render per rank + NCCL gather + rrt_assemble_bands + D2H to pinned host"))},
         "gpu_launches": launches,
+        "pipeline": ({"kind": "split: trace / media / fold kernels over a sample pool in HBM (csrc/rrt_split.cuh)",
+                      "passes_per_frame": split["passes_worked"], "passes_enqueued": split["passes_enqueued"],
+                      "tiles_left_to_fused_sweep": split["tiles_swept"], "pool_GiB_per_stream": split["pool_kislots"] * 32 / 2 ** 20}
+                     if split["passes_enqueued"] else {"kind": "fused: render_kernel"}),
         "clocks": clk.summary(),
     }
 

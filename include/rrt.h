@@ -183,6 +183,32 @@ int rrt_render_host_async(rrt_context* ctx, const rrt_params* prm, const rrt_cam
  * the start instead of each filling the GPU and ending in a drain; results do not depend on it. */
 int rrt_set_frames_in_flight(rrt_context* ctx, int n);
 
+/* ---- render pipeline ------------------------------------------------------------------------------------------
+ * A launch with a medium (RRT_FLAG_DISK / RRT_FLAG_DUST) can run as ONE fused kernel (every in-zone step evaluates
+ * its media sample on the spot, like the reference's raymarch_kernel, src/raymarcher.cu:67-115) or SPLIT into three
+ * kernels per pass over a sample pool in device memory: trace (trajectories; in-zone steps append their sample to the
+ * pool), media (one thread per sample, densely packed) and fold (per ray, `I += e (1 - s) T; T *= s` in step order,
+ * then background / effects / store).  Media samples do not feed back into the trajectory, so both produce the same
+ * bits; the split form removes the frame's longest dependency chain (a disk-plane ray: 2000 x (step + both media))
+ * and evaluates the media with every lane busy.  AUTO = split whenever a medium is on and the pool can be allocated.
+ * RRT_PIPELINE=auto|fused|split in the environment sets the default of new contexts. */
+#define RRT_PIPELINE_AUTO 0
+#define RRT_PIPELINE_FUSED 1
+#define RRT_PIPELINE_SPLIT 2
+int rrt_set_pipeline(rrt_context* ctx, int mode);
+/* Sample pool of the split pipeline: one pool per stream in flight (up to RRT_HOST_SLOTS), each at most
+ * max_bytes_per_stream (default 8 GiB, RRT_POOL_MB; sized to the frame: 2 KiB per pixel, at least 32 MiB).  A frame that
+ * needs more is rendered in several passes (at most max_passes, default 32, RRT_MAX_PASSES; whatever is left after them
+ * is rendered by the fused code), so any size gives the same frame.  0 leaves a value unchanged. */
+int rrt_set_sample_pool(rrt_context* ctx, size_t max_bytes_per_stream, int max_passes);
+/* Synchronises and reports the split pipeline's bookkeeping of the last frame that completed: [0] passes that traced
+ * tiles, [1] tiles left to the closing fused sweep, [2] tiles traced by the passes, [3] passes enqueued, [4] tiles of
+ * the launch, [5] pool size in Ki slots of 32 bytes; all 0 when no frame went through the split pipeline. */
+int rrt_split_stats(rrt_context* ctx, uint32_t out[8]);
+/* Kernels this context has launched so far for rrt_render* and rrt_assemble_bands (1 per fused frame; 3 per pass + 1
+ * per split frame): what a benchmark reports as its launch count. */
+uint64_t rrt_kernel_launches(rrt_context* ctx);
+
 /* Number of rows a band owns in an h-row image (packed buffer height). */
 int rrt_band_rows(const rrt_band* band, int h);
 

@@ -19,6 +19,7 @@ CLS_CAPTURED, CLS_DISK_HIT, CLS_ESCAPED, CLS_MASK = 0, 1, 2, 3
 CLSF_EXHAUSTED, CLSF_TOUCHED = 4, 8
 OUT_FRAME, OUT_PACKED = 0, 1
 HOST_SLOTS = 4   # RRT_HOST_SLOTS
+PIPELINE_AUTO, PIPELINE_FUSED, PIPELINE_SPLIT = 0, 1, 2
 
 
 class RrtError(RuntimeError):
@@ -77,7 +78,7 @@ SYMBOLS = [
     "rrt_path_state", "rrt_path_clock", "rrt_exact_math_selftest", "rrt_exact_pow_selftest",
     "rrt_image_load", "rrt_image_decode", "rrt_image_free", "rrt_image_last_error", "rrt_sky_load",
     "rrt_peer_frame_create", "rrt_peer_frame_open", "rrt_peer_frame_read", "rrt_peer_frame_close",
-    "rrt_debug_tile_log", "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
+    "rrt_debug_tile_log", "rrt_set_probe_contract", "rrt_set_frames_in_flight", "rrt_set_pipeline", "rrt_set_sample_pool", "rrt_split_stats", "rrt_kernel_launches", "rrt_sink_open", "rrt_sink_write", "rrt_sink_frames", "rrt_sink_close", "rrt_sink_ffmpeg_command",
 ]
 
 _lib = None
@@ -155,6 +156,11 @@ def load() -> C.CDLL:
     lib.rrt_debug_tile_log.argtypes = [vp, vp, C.c_size_t]
     lib.rrt_set_probe_contract.argtypes = [vp, ci]
     lib.rrt_set_frames_in_flight.argtypes = [vp, ci]
+    lib.rrt_set_pipeline.argtypes = [vp, ci]
+    lib.rrt_set_sample_pool.argtypes = [vp, C.c_size_t, ci]
+    lib.rrt_split_stats.argtypes = [vp, P(C.c_uint32)]
+    lib.rrt_kernel_launches.argtypes = [vp]
+    lib.rrt_kernel_launches.restype = C.c_uint64
     lib.rrt_sink_open.argtypes = [C.c_char_p, ci, ci, ci, ci, P(vp)]
     lib.rrt_sink_write.argtypes = [vp, vp]
     lib.rrt_sink_frames.argtypes = [vp]

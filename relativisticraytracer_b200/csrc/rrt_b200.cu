@@ -143,6 +143,27 @@ struct rrt_context {
     unsigned tile_log_cap = 0;
     bool probe_fmad = true;   // contract of the parameter-less probes (hash31 / noise3D / fbm): like rrt_default_params
     int frames_in_flight = 1; // render launches expected to run concurrently: each gets 1/n of the resident-CTA slots
+    // split pipeline (csrc/rrt_split.cuh): trace / media / fold kernels over a sample pool, one pool per stream in flight
+    int pipeline = RRT_PIPELINE_AUTO;
+    size_t pool_bytes_max = 8ull << 30;   // per pool (RRT_POOL_MB / rrt_set_sample_pool)
+    int max_passes = 32;
+    struct SamplePool {
+        bool in_use = false;
+        cudaStream_t stream = nullptr;
+        uint4* d_slots = nullptr;
+        size_t cap_slots = 0;
+        unsigned* d_chunk_used = nullptr;
+        size_t chunk_used_entries = 0;
+        char* d_ctrl = nullptr;           // PassCtrl[kMaxPasses + 1] | stats[8] | redo lists
+        rrtk::PendTile* d_pend = nullptr;
+        size_t pend_cap = 0;
+        unsigned* h_stats = nullptr;      // pinned copy of the stats of the last frame that completed on this pool
+        cudaEvent_t done = nullptr;
+        unsigned long long last_use = 0;
+    };
+    SamplePool pools[RRT_HOST_SLOTS];
+    unsigned long long pool_clock = 0;
+    unsigned long long launches = 0;      // kernels this context has launched for rrt_render* / rrt_assemble_bands
     std::string err;
     std::mutex mu;
 };
@@ -153,6 +174,12 @@ struct rrt_sky {
 };
 
 namespace {
+constexpr int kMaxPasses = 32;          // split passes one frame can be cut into (then the sweep takes what is left)
+constexpr unsigned kRedoCap = 16384;    // tiles one pass can give up: at most one per tracing warp
+constexpr size_t kSlotBytes = 32;
+constexpr size_t kPoolPadSlots = 64;    // fold_kernel reads a 33-slot window from any record header
+constexpr size_t kCtrlHead = sizeof(rrtk::PassCtrl) * (kMaxPasses + 1) + 8 * sizeof(unsigned);   // zeroed per frame
+constexpr size_t kCtrlBytes = kCtrlHead + sizeof(unsigned) * kRedoCap * (kMaxPasses + 1);
 constexpr unsigned kTicketRing = 1024;
 thread_local std::string g_create_err;
 
@@ -273,6 +300,9 @@ int rrt_context_create(int device, rrt_context** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* k = std::getenv("RRT_KERNEL")) ctx->kernel_choice = !std::strcmp(k, "packed") ? 2 : (!std::strcmp(k, "scalar") ? 1 : 0);
+    if (const char* k = std::getenv("RRT_PIPELINE")) ctx->pipeline = !std::strcmp(k, "split") ? RRT_PIPELINE_SPLIT : (!std::strcmp(k, "fused") ? RRT_PIPELINE_FUSED : RRT_PIPELINE_AUTO);
+    if (const char* k = std::getenv("RRT_POOL_MB")) { const long long mb = std::atoll(k); if (mb > 0) ctx->pool_bytes_max = (size_t)mb << 20; }
+    if (const char* k = std::getenv("RRT_MAX_PASSES")) { const int n = std::atoi(k); if (n >= 1 && n <= kMaxPasses) ctx->max_passes = n; }
 #ifdef RRT_WITH_VARIANTS
     if (const char* kv = std::getenv("RRT_KERNEL_VARIANT")) {
         const int k = std::atoi(kv);
@@ -300,6 +330,14 @@ void rrt_context_destroy(rrt_context* ctx) {
     if (ctx->d_tickets) cudaFree(ctx->d_tickets);
     for (void* f : ctx->d_frame)
         if (f) cudaFree(f);
+    for (auto& pl : ctx->pools) {
+        if (pl.d_slots) cudaFree(pl.d_slots);
+        if (pl.d_chunk_used) cudaFree(pl.d_chunk_used);
+        if (pl.d_ctrl) cudaFree(pl.d_ctrl);
+        if (pl.d_pend) cudaFree(pl.d_pend);
+        if (pl.h_stats) cudaFreeHost(pl.h_stats);
+        if (pl.done) cudaEventDestroy(pl.done);
+    }
     delete ctx;
 }
 
@@ -391,6 +429,149 @@ int rrt_band_rows(const rrt_band* band, int h) {
     return rows;
 }
 
+
+// ---- split pipeline: host side (csrc/rrt_split.cuh) ---------------------------------------------------------------
+// Resident CTAs per SM of a kernel, asked for once per context (see rrt_render).
+static int resident_per_sm(rrt_context* ctx, const void* kern, int block, bool max_shared) {
+    for (int i = 0; i < ctx->n_launch_cfg; ++i)
+        if (ctx->launch_cfg[i].kern == kern) return ctx->launch_cfg[i].per_sm;
+    int per_sm = 0;
+    if (max_shared) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (ctx->n_launch_cfg < 16) ctx->launch_cfg[ctx->n_launch_cfg++] = {kern, per_sm};
+    return per_sm;
+}
+
+// The pool this stream renders through: its own if it has one, else a free one, else the least recently used one
+// (stream-ordered behind that pool's last frame).  (Re)allocated when the frame needs more than it holds.  Returns null,
+// with no error set, when the memory is not there: the caller renders fused.
+static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, long long local_pixels, unsigned ntiles) {
+    rrt_context::SamplePool* pl = nullptr;
+    for (auto& c : ctx->pools)
+        if (c.in_use && c.stream == st) pl = &c;
+    if (!pl)
+        for (auto& c : ctx->pools)
+            if (!c.in_use && !pl) pl = &c;
+    if (!pl) {
+        for (auto& c : ctx->pools)
+            if (!pl || c.last_use < pl->last_use) pl = &c;
+        if (pl->done && cudaStreamWaitEvent(st, pl->done, 0) != cudaSuccess) return nullptr;
+    }
+    size_t want_bytes = (size_t)local_pixels * 2048;   // ~64 samples per pixel before a frame is cut into passes
+    if (want_bytes < (32ull << 20)) want_bytes = 32ull << 20;
+    if (want_bytes > ctx->pool_bytes_max) want_bytes = ctx->pool_bytes_max;
+    size_t want_slots = want_bytes / kSlotBytes;
+    if (want_slots > 0xfff00000ull) want_slots = 0xfff00000ull;   // slot indices are 32-bit
+    if (want_slots < 1024) want_slots = 1024;
+    const bool fresh = !pl->in_use;
+    const size_t max_slots = ctx->pool_bytes_max / kSlotBytes;
+    const bool resize = pl->cap_slots < want_slots || pl->cap_slots > (max_slots > want_slots ? max_slots : want_slots);   // grows; shrinks only below a lowered limit
+    if (resize || pl->pend_cap < ntiles || !pl->d_ctrl) {
+        if (pl->done) cudaEventSynchronize(pl->done);
+        if (resize) {
+            if (pl->d_slots) cudaFree(pl->d_slots);
+            if (pl->d_chunk_used) cudaFree(pl->d_chunk_used);
+            pl->d_slots = nullptr; pl->d_chunk_used = nullptr; pl->cap_slots = 0;
+            pl->chunk_used_entries = want_slots / 256 + 1;   // 256 = the smallest chunk
+            if (cudaMalloc(&pl->d_slots, (want_slots + kPoolPadSlots) * kSlotBytes) != cudaSuccess ||
+                cudaMalloc(&pl->d_chunk_used, pl->chunk_used_entries * sizeof(unsigned)) != cudaSuccess ||
+                cudaMemset(pl->d_slots, 0, (want_slots + kPoolPadSlots) * kSlotBytes) != cudaSuccess) {
+                cudaGetLastError();
+                if (pl->d_slots) cudaFree(pl->d_slots);
+                if (pl->d_chunk_used) cudaFree(pl->d_chunk_used);
+                pl->d_slots = nullptr; pl->d_chunk_used = nullptr;
+                return nullptr;
+            }
+            pl->cap_slots = want_slots;
+        }
+        if (pl->pend_cap < ntiles) {
+            if (pl->d_pend) cudaFree(pl->d_pend);
+            pl->d_pend = nullptr; pl->pend_cap = 0;
+            if (cudaMalloc(&pl->d_pend, (size_t)ntiles * sizeof(rrtk::PendTile)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            pl->pend_cap = ntiles;
+        }
+        if (!pl->d_ctrl) {
+            if (cudaMalloc(&pl->d_ctrl, kCtrlBytes) != cudaSuccess || cudaMallocHost(&pl->h_stats, 8 * sizeof(unsigned)) != cudaSuccess ||
+                cudaEventCreateWithFlags(&pl->done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            std::memset(pl->h_stats, 0, 8 * sizeof(unsigned));
+        }
+    }
+    if (fresh || pl->stream != st) std::memset(pl->h_stats, 0, 8 * sizeof(unsigned));   // another stream's history says nothing
+    pl->in_use = true;
+    pl->stream = st;
+    pl->last_use = ++ctx->pool_clock;
+    return pl;
+}
+
+// One frame through trace / media / fold passes and the closing sweep.  `grid_trace` = the persistent grid of the
+// tracing kernels for this launch (already divided by the frames in flight).
+static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fmad, long long grid_trace, cudaStream_t st,
+                        rrt_context::SamplePool* pl) {
+    const rrtk::SplitKernels* sk = fmad ? rrtk::rrt_split_kernels_fmad() : rrtk::rrt_split_kernels_strict();
+    auto k_trace = sk->trace[spin ? 1 : 0];
+    auto k_sweep = sk->sweep[spin ? 1 : 0];
+    const unsigned ntiles = (unsigned)(((A.w + kRTileW - 1) / kRTileW) * ((A.local_rows + kRTileH - 1) / kRTileH));
+
+    // passes to enqueue: what the last completed frame on this pool needed (the sweep renders whatever a wrong guess leaves)
+    const unsigned* hs = pl->h_stats;   // [0] passes that took tiles [1] tiles swept [2] tiles taken by passes [3] passes enqueued [4] ntiles
+    int passes = 2;
+    if (hs[3] != 0u) {
+        if (hs[1] == 0u) passes = (int)hs[0];
+        else passes = (int)(((unsigned long long)hs[3] * hs[4] + hs[2]) / (hs[2] ? hs[2] : 1u)) + 1;
+    }
+    if (passes < 1) passes = 1;
+    if (passes > ctx->max_passes) passes = ctx->max_passes;
+
+    rrtk::SplitArgs S;
+    std::memset(&S, 0, sizeof(S));
+    S.slots = pl->d_slots;
+    S.capacity = (unsigned)pl->cap_slots;
+    unsigned chunk = 4096;
+    while (chunk > 256 && (unsigned long long)chunk * 8ull * (unsigned long long)grid_trace > pl->cap_slots) chunk >>= 1;
+    S.chunk_slots = chunk;
+    S.chunk_shift = 0;
+    while ((1u << S.chunk_shift) < chunk) ++S.chunk_shift;
+    unsigned long long head = (unsigned long long)grid_trace * 16384ull;
+    if (head > pl->cap_slots / 4) head = pl->cap_slots / 4;
+    S.high_water = (unsigned)(pl->cap_slots - head);
+    S.chunk_used = pl->d_chunk_used;
+    S.pend = pl->d_pend;
+    S.redo_cap = kRedoCap;
+    rrtk::PassCtrl* pcs = (rrtk::PassCtrl*)pl->d_ctrl;
+    S.stats = (unsigned*)(pl->d_ctrl + sizeof(rrtk::PassCtrl) * (kMaxPasses + 1));
+    unsigned* redo = (unsigned*)(pl->d_ctrl + kCtrlHead);
+    const size_t chunk_entries = pl->cap_slots / chunk + 1;
+
+    RRT_CU(ctx, cudaMemsetAsync(pl->d_ctrl, 0, kCtrlHead, st));
+    const int per_sm_media = resident_per_sm(ctx, (const void*)sk->media, kMediaBlock, false);
+    const int per_sm_fold = resident_per_sm(ctx, (const void*)sk->fold, 128, false);
+    const int per_sm_sweep = resident_per_sm(ctx, (const void*)k_sweep, kRenderBlock, true);
+    for (int p = 0; p < passes; ++p) {
+        S.pass = (unsigned)p;
+        S.pc = pcs + p;
+        S.pc_prev = p ? pcs + (p - 1) : nullptr;
+        S.redo_in = p ? redo + (size_t)(p - 1) * kRedoCap : nullptr;
+        S.redo_out = redo + (size_t)p * kRedoCap;
+        RRT_CU(ctx, cudaMemsetAsync(pl->d_chunk_used, 0, chunk_entries * sizeof(unsigned), st));
+        k_trace<<<(unsigned)grid_trace, kRenderBlock, 0, st>>>(A, S);
+        sk->media<<<(unsigned)(ctx->sm_count * per_sm_media), kMediaBlock, 0, st>>>(A, S);
+        sk->fold<<<(unsigned)(ctx->sm_count * per_sm_fold), 128, 0, st>>>(A, S);
+    }
+    S.pass = (unsigned)passes;
+    S.pc = pcs + passes;
+    S.pc_prev = pcs + (passes - 1);
+    S.redo_in = redo + (size_t)(passes - 1) * kRedoCap;
+    S.redo_out = redo + (size_t)passes * kRedoCap;
+    long long grid_sweep = ((long long)ctx->sm_count * per_sm_sweep + ctx->frames_in_flight - 1) / ctx->frames_in_flight;
+    if (grid_sweep > (long long)ntiles) grid_sweep = ntiles;
+    k_sweep<<<(unsigned)grid_sweep, kRenderBlock, 0, st>>>(A, S);
+    RRT_CU(ctx, cudaGetLastError());
+    ctx->launches += 3ull * (unsigned)passes + 1ull;
+    RRT_CU(ctx, cudaMemcpyAsync(pl->h_stats, S.stats, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    RRT_CU(ctx, cudaEventRecord(pl->done, st));
+    return RRT_OK;
+}
+
 int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, const rrt_effects* fx, uint64_t sky_texture,
                float time, int w, int h, const rrt_band* band, void* d_out, int out_layout, const rrt_planes* planes,
                void* stream) {
@@ -471,8 +652,22 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     long long grid = ((long long)ctx->sm_count * per_sm + ctx->frames_in_flight - 1) / ctx->frames_in_flight;
     const long long need = ((long long)w * local_rows + rays_per_block - 1) / rays_per_block;
     if (grid > need) grid = need;
+    // A launch with a medium goes through the split pipeline (csrc/rrt_split.cuh) unless the caller pinned the fused
+    // kernel, a measured variant or the tile log is selected, or the pool cannot be allocated.
+    if (media && variant == 1 && ctx->pipeline != RRT_PIPELINE_FUSED && (!ctx->tile_log || ctx->pipeline == RRT_PIPELINE_SPLIT) && prm->max_steps < (1 << 28)) {
+        const rrtk::SplitKernels* sk = fmad ? rrtk::rrt_split_kernels_fmad() : rrtk::rrt_split_kernels_strict();
+        const int per_sm_trace = resident_per_sm(ctx, (const void*)sk->trace[spin ? 1 : 0], kRenderBlock, true);
+        const unsigned ntiles = (unsigned)(((w + kRTileW - 1) / kRTileW) * ((local_rows + kRTileH - 1) / kRTileH));
+        long long grid_trace = ((long long)ctx->sm_count * per_sm_trace + ctx->frames_in_flight - 1) / ctx->frames_in_flight;
+        if (grid_trace > (long long)ntiles) grid_trace = ntiles;
+        if (grid_trace > (long long)kRedoCap) grid_trace = kRedoCap;
+        if (rrt_context::SamplePool* pl = acquire_pool(ctx, st, (long long)w * local_rows, ntiles))
+            return render_split(ctx, A, spin, fmad, grid_trace, st, pl);
+        if (ctx->pipeline == RRT_PIPELINE_SPLIT) return fail(ctx, RRT_ERR_NOMEM, "rrt_render: no memory for the sample pool of the split pipeline");
+    }
     kern<<<(unsigned)grid, block, 0, st>>>(A);
     RRT_CU(ctx, cudaGetLastError());
+    ctx->launches += 1;
     return RRT_OK;
 }
 
@@ -520,6 +715,7 @@ int rrt_assemble_bands(rrt_context* ctx, const void* d_packed, int rows_per_rank
     assemble_kernel<<<ctx->sm_count * 8, 256, 0, (cudaStream_t)stream>>>((const uchar4*)d_packed, rows_per_rank, w, h,
                                                                          nranks, group, (uchar4*)d_frame);
     RRT_CU(ctx, cudaGetLastError());
+    { std::lock_guard<std::mutex> lk(ctx->mu); ctx->launches += 1; }
     return RRT_OK;
 }
 
@@ -686,6 +882,45 @@ int rrt_sky_sample_batch(rrt_context* ctx, uint64_t sky_texture, int n, const fl
     int rc = run_probe(ctx, n, k_sky, (cudaTextureObject_t)sky_texture, n, (const float*)dx.p, (const float*)dy.p, (float4*)dout.p);
     if (rc) return rc;
     RRT_CU(ctx, cudaMemcpy(out4, dout.p, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RRT_OK;
+}
+
+uint64_t rrt_kernel_launches(rrt_context* ctx) {
+    if (!ctx) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return ctx->launches;
+}
+
+int rrt_set_pipeline(rrt_context* ctx, int mode) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (mode != RRT_PIPELINE_AUTO && mode != RRT_PIPELINE_FUSED && mode != RRT_PIPELINE_SPLIT) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_set_pipeline: bad mode");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->pipeline = mode;
+    return RRT_OK;
+}
+
+int rrt_set_sample_pool(rrt_context* ctx, size_t max_bytes_per_stream, int max_passes) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (max_passes < 0 || max_passes > kMaxPasses) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_set_sample_pool: max_passes out of range");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (max_bytes_per_stream) ctx->pool_bytes_max = max_bytes_per_stream;
+    if (max_passes) ctx->max_passes = max_passes;
+    return RRT_OK;
+}
+
+int rrt_split_stats(rrt_context* ctx, uint32_t out[8]) {
+    if (!ctx) return RRT_ERR_BAD_ARG;
+    if (!out) return fail(ctx, RRT_ERR_BAD_ARG, "rrt_split_stats: out is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DevGuard g(ctx->device);
+    RRT_CU(ctx, cudaDeviceSynchronize());
+    const rrt_context::SamplePool* last = nullptr;
+    for (const auto& pl : ctx->pools)
+        if (pl.in_use && (!last || pl.last_use > last->last_use)) last = &pl;
+    for (int i = 0; i < 8; ++i) out[i] = last ? last->h_stats[i] : 0u;
+    if (last) {
+        out[5] = (uint32_t)(last->cap_slots >> 10);   // pool size in Ki slots (32 B each)
+    }
     return RRT_OK;
 }
 

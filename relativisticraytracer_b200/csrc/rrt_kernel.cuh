@@ -96,6 +96,15 @@ constexpr int kRenderBlock = RRT_RENDER_BLOCK;
 #define RRT_MIN_BLOCKS_MEDIA (6 * 128 / RRT_RENDER_BLOCK)
 #endif
 
+#ifdef RRT_WITH_GROUP_STEPS
+// profiling build (-DRRT_WITH_TILE_LOG -DRRT_WITH_GROUP_STEPS): how many times a warp EXECUTED the checked step for a tile (one count per group of lanes that run it
+// together): equals the longest ray's checked steps while the tile's lanes stay converged
+__shared__ unsigned g_dbg_group_steps[8];
+__device__ __forceinline__ unsigned dbg_group_steps(int warp) { return min(g_dbg_group_steps[warp], 0xfffffu); }
+#else
+__device__ __forceinline__ unsigned dbg_group_steps(int) { return 0u; }
+#endif
+
 struct RayResult {
     float hdr[3], T, I[3];
     V3 d, p, v;
@@ -258,9 +267,21 @@ __device__ __noinline__ void finish_ray(const FrameArgs& A, int x, int y, int ly
     finish_ray_inl(A, x, y, ly, uvx, uvy, Ir, Ig, Ib, T, p, v, steps, end);
 }
 
+// What trace_ray does with an in-zone step's media sample (reference :67-115):
+//   kMediaNone    nothing (no medium requested)
+//   kMediaInline  evaluates it on the spot and folds it into I / T (the fused render_kernel)
+//   kMediaEmit    hands (pre-step position, post-step velocity, radius, zone) to an emitter -- the split pipeline of
+//                 rrt_split.cuh, where a second kernel evaluates the samples of many rays densely packed and a third
+//                 folds the results in step order.  Samples do not feed back into the trajectory, so all three modes
+//                 trace the same ray.
+enum : int { kMediaNone = 0, kMediaInline = 1, kMediaEmit = 2 };
+struct NoEmit {
+    __device__ __forceinline__ void emit(V3, V3, float, int, unsigned) {}
+};
+
 // One ray: reference raymarch_kernel lines 20-150.
-template <bool SPIN, bool MEDIA>
-__device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayResult& R) {
+template <bool SPIN, int MEDIA, class EM>
+__device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayResult& R, EM& em) {
     const Consts& C = A.C;
     float uvx, uvy;
     pixel_uv(A, x, y, uvx, uvy);                                       // :20-25
@@ -281,7 +302,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
     // the whole ray outside the fast domain (+inf: every step is redone)
     const float redo_below = fast_ok ? C.acc_rmin : __int_as_float(0x7f800000);
 #if RRT_BURST_K > 0
-    constexpr int kBurst = RRT_BURST_K, kBurstUnroll = MEDIA ? RRT_BURST_UNROLL_MEDIA : RRT_BURST_UNROLL;
+    constexpr int kBurst = RRT_BURST_K, kBurstUnroll = MEDIA == kMediaInline ? RRT_BURST_UNROLL_MEDIA : RRT_BURST_UNROLL;
     static_assert(kBurst % kBurstUnroll == 0, "burst length must be a multiple of its unroll factor");
     // every threshold a checked vacuum step compares a radius against from above: zones (:56-58), horizon (:47),
     // geodesics.h:33 through the redo guard
@@ -368,6 +389,9 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
         bool rewind = false;
 #pragma unroll 1
         while (it < max_steps) {                                                              // :41
+#ifdef RRT_WITH_GROUP_STEPS
+            if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicAdd(&g_dbg_group_steps[threadIdx.x >> 5], 1u);
+#endif
             if (r < C.horizon_r) { ev = kCaptured; break; }                                   // :47-51
             unsigned z = 0;
             float rmin;
@@ -379,7 +403,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 #ifdef RRT_TWO_CHECKED   // A/B knob: keep the constant-step copy of the checked vacuum step in the media kernels too
             constexpr bool kOneCheckedStep = !RRT_FMAD;
 #else
-            constexpr bool kOneCheckedStep = !RRT_FMAD || (MEDIA && RRT_BURST_K > 0);
+            constexpr bool kOneCheckedStep = !RRT_FMAD || (MEDIA == kMediaInline && RRT_BURST_K > 0);
 #endif
             if (kOneCheckedStep || r < zone_rmax) {
                 float h = C.h[0], h6 = C.h6[0];
@@ -410,10 +434,11 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             ++it;
             const float r2_next = rrt::norm2_loop(p);
             const float r_next = rrt::sqrt_rn_fast(r2_next);
-            if (MEDIA && z) {
+            if (MEDIA != kMediaNone && z) {
                 n_disk += z & 1u;
                 n_dust += z >> 1;
-                fold(media_sample(C, q, v, r, C.h[zone_index], A.time, z));
+                if (MEDIA == kMediaInline) fold(media_sample(C, q, v, r, C.h[zone_index], A.time, z));
+                else em.emit(q, v, r, zone_index, z);
             }
             if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { ev = kEscaped; break; }               // :120
             r2 = r2_next;
@@ -432,10 +457,11 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
             const PV s = rk4_step_general<SPIN>(C, q, v_in, h, h * 0.5f, C.h6[zone_index]);
             p = s.p; v = s.v;
             ++it;
-            if (MEDIA && zones) {
+            if (MEDIA != kMediaNone && zones) {
                 n_disk += zones & 1u;
                 n_dust += zones >> 1;
-                fold(media_sample(C, q, v, r, h, A.time, zones));
+                if (MEDIA == kMediaInline) fold(media_sample(C, q, v, r, h, A.time, zones));
+                else em.emit(q, v, r, zone_index, zones);
             }
             if (r > 250.0f && rrt::dot3(q, v) > 0.0f) { escaped = true; break; }              // :120
             continue;
@@ -485,9 +511,15 @@ __global__ void __launch_bounds__(kRenderBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : R
 #ifdef RRT_WITH_TILE_LOG
         unsigned long long t_begin = 0;
         if (A.tile_log) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#ifdef RRT_WITH_GROUP_STEPS
+        __syncwarp();
+        if (lane == 0) g_dbg_group_steps[threadIdx.x >> 5] = 0u;
+        __syncwarp();
+#endif
 #endif
         RayResult R;
-        trace_ray<SPIN, MEDIA>(A, x, y, R);
+        NoEmit no_emit;
+        trace_ray<SPIN, MEDIA ? kMediaInline : kMediaNone>(A, x, y, R, no_emit);
 
         finish_ray_inl(A, x, y, ly, R.uvx, R.uvy, R.I[0], R.I[1], R.I[2], R.T, R.p, R.v, R.steps,
                        (R.captured ? kEndCaptured : 0u) | (R.touched ? kEndTouched : 0u) | (R.exhausted ? kEndExhausted : 0u));
@@ -503,7 +535,8 @@ __global__ void __launch_bounds__(kRenderBlock, MEDIA ? RRT_MIN_BLOCKS_MEDIA : R
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
                 unsigned long long* e = A.tile_log + 4ull * tile;
-                e[0] = t_begin; e[1] = t_end; e[2] = ((unsigned long long)ty << 32) | (unsigned)tx; e[3] = ((unsigned long long)smid << 32) | (unsigned)most;
+                e[0] = t_begin; e[1] = t_end; e[2] = ((unsigned long long)ty << 32) | (unsigned)tx;
+                e[3] = ((unsigned long long)smid << 32) | (unsigned)most | (dbg_group_steps(threadIdx.x >> 5) << 12);
             }
         }
 #endif
@@ -598,6 +631,7 @@ __global__ void k_sky(cudaTextureObject_t sky, int n, const float* tx, const flo
 #if RRT_FMAD
 #include "rrt_packed.cuh"
 #endif
+#include "rrt_split.cuh"   // trace / media / fold kernels of the split pipeline (both contracts)
 namespace {
 const rrtk::KernelSet kKernelSet = {
     {{render_kernel<false, false>, render_kernel<false, true>}, {render_kernel<true, false>, render_kernel<true, true>}},

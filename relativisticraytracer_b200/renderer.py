@@ -240,6 +240,27 @@ class Renderer:
         """rrt_set_frames_in_flight: each launch takes 1/n of the resident-CTA slots (n concurrent frames)."""
         self._check(self._lib.rrt_set_frames_in_flight(self._ctx, int(n)))
 
+    def set_pipeline(self, mode) -> None:
+        """rrt_set_pipeline: "auto" (split whenever a medium is on), "fused" (one kernel) or "split"
+        (trace / media / fold kernels over the sample pool); same frames either way."""
+        modes = {"auto": _capi.PIPELINE_AUTO, "fused": _capi.PIPELINE_FUSED, "split": _capi.PIPELINE_SPLIT}
+        self._check(self._lib.rrt_set_pipeline(self._ctx, int(modes.get(mode, mode))))
+
+    def set_sample_pool(self, max_bytes_per_stream: int = 0, max_passes: int = 0) -> None:
+        """rrt_set_sample_pool: size limit of one sample pool and the passes a frame may be cut into (0 = unchanged)."""
+        self._check(self._lib.rrt_set_sample_pool(self._ctx, C.c_size_t(int(max_bytes_per_stream)), int(max_passes)))
+
+    def kernel_launches(self) -> int:
+        """rrt_kernel_launches: kernels launched so far by this context's render / assemble calls."""
+        return int(self._lib.rrt_kernel_launches(self._ctx))
+
+    def split_stats(self) -> dict:
+        """rrt_split_stats: bookkeeping of the last frame the split pipeline completed (synchronises)."""
+        out = (C.c_uint32 * 8)()
+        self._check(self._lib.rrt_split_stats(self._ctx, out))
+        return {"passes_worked": int(out[0]), "tiles_swept": int(out[1]), "tiles_split": int(out[2]),
+                "passes_enqueued": int(out[3]), "tiles": int(out[4]), "pool_kislots": int(out[5])}
+
     def tile_log(self, log: Optional[torch.Tensor]) -> None:
         """rrt_debug_tile_log: per-tile (start ns, end ns, row<<32|col, sm<<32|max steps) into `log` ([n, 4] int64/uint64
         device tensor), or None to switch it off."""
