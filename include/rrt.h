@@ -197,7 +197,7 @@ int rrt_set_frames_in_flight(rrt_context* ctx, int n);
 #define RRT_PIPELINE_SPLIT 2
 int rrt_set_pipeline(rrt_context* ctx, int mode);
 /* Sample pool of the split pipeline: one pool per stream in flight (up to RRT_HOST_SLOTS), each at most
- * max_bytes_per_stream (default 8 GiB, RRT_POOL_MB; sized to the frame: 2 KiB per pixel, at least 32 MiB).  A frame that
+ * max_bytes_per_stream (default 16 GiB, RRT_POOL_MB; sized to the frame: 4 KiB per pixel plus ~2 MiB per resident tracing warp, at least 64 MiB).  A frame that
  * needs more is rendered in several passes (at most max_passes, default 32, RRT_MAX_PASSES; whatever is left after them
  * is rendered by the fused code), so any size gives the same frame.  0 leaves a value unchanged. */
 int rrt_set_sample_pool(rrt_context* ctx, size_t max_bytes_per_stream, int max_passes);

@@ -145,18 +145,18 @@ struct rrt_context {
     int frames_in_flight = 1; // render launches expected to run concurrently: each gets 1/n of the resident-CTA slots
     // split pipeline (csrc/rrt_split.cuh): trace / media / fold kernels over a sample pool, one pool per stream in flight
     int pipeline = RRT_PIPELINE_AUTO;
-    size_t pool_bytes_max = 8ull << 30;   // per pool (RRT_POOL_MB / rrt_set_sample_pool)
+    size_t pool_bytes_max = 16ull << 30;  // per pool (RRT_POOL_MB / rrt_set_sample_pool)
     int max_passes = 32;
     struct SamplePool {
         bool in_use = false;
         cudaStream_t stream = nullptr;
         uint4* d_slots = nullptr;
         size_t cap_slots = 0;
-        unsigned* d_chunk_used = nullptr;
-        size_t chunk_used_entries = 0;
         char* d_ctrl = nullptr;           // PassCtrl[kMaxPasses + 1] | stats[8] | redo lists
-        rrtk::PendTile* d_pend = nullptr;
-        size_t pend_cap = 0;
+        rrtk::TileDesc* d_desc = nullptr; // one per tile a pass can queue
+        size_t desc_cap = 0;
+        rrtk::WorkItem* d_work = nullptr; // media work items of one pass
+        size_t work_cap = 0;
         unsigned* h_stats = nullptr;      // pinned copy of the stats of the last frame that completed on this pool
         cudaEvent_t done = nullptr;
         unsigned long long last_use = 0;
@@ -332,9 +332,9 @@ void rrt_context_destroy(rrt_context* ctx) {
         if (f) cudaFree(f);
     for (auto& pl : ctx->pools) {
         if (pl.d_slots) cudaFree(pl.d_slots);
-        if (pl.d_chunk_used) cudaFree(pl.d_chunk_used);
         if (pl.d_ctrl) cudaFree(pl.d_ctrl);
-        if (pl.d_pend) cudaFree(pl.d_pend);
+        if (pl.d_desc) cudaFree(pl.d_desc);
+        if (pl.d_work) cudaFree(pl.d_work);
         if (pl.h_stats) cudaFreeHost(pl.h_stats);
         if (pl.done) cudaEventDestroy(pl.done);
     }
@@ -445,7 +445,7 @@ static int resident_per_sm(rrt_context* ctx, const void* kern, int block, bool m
 // The pool this stream renders through: its own if it has one, else a free one, else the least recently used one
 // (stream-ordered behind that pool's last frame).  (Re)allocated when the frame needs more than it holds.  Returns null,
 // with no error set, when the memory is not there: the caller renders fused.
-static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, long long local_pixels, unsigned ntiles) {
+static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, long long local_pixels, unsigned ntiles, long long grid_trace, int max_steps) {
     rrt_context::SamplePool* pl = nullptr;
     for (auto& c : ctx->pools)
         if (c.in_use && c.stream == st) pl = &c;
@@ -457,8 +457,10 @@ static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, 
             if (!pl || c.last_use < pl->last_use) pl = &c;
         if (pl->done && cudaStreamWaitEvent(st, pl->done, 0) != cudaSuccess) return nullptr;
     }
-    size_t want_bytes = (size_t)local_pixels * 2048;   // ~64 samples per pixel before a frame is cut into passes
-    if (want_bytes < (32ull << 20)) want_bytes = 32ull << 20;
+    // ~128 samples per pixel before a frame is cut into passes, plus what the tracing warps hold in reserve: each takes
+    // the rows its tile could need in the worst case (max_steps + 1 rows of 1 KiB) before it traces it
+    size_t want_bytes = (size_t)local_pixels * 4096 + (size_t)grid_trace * ((size_t)max_steps + 2 + 256) * 1024;
+    if (want_bytes < (64ull << 20)) want_bytes = 64ull << 20;
     if (want_bytes > ctx->pool_bytes_max) want_bytes = ctx->pool_bytes_max;
     size_t want_slots = want_bytes / kSlotBytes;
     if (want_slots > 0xfff00000ull) want_slots = 0xfff00000ull;   // slot indices are 32-bit
@@ -466,29 +468,26 @@ static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, 
     const bool fresh = !pl->in_use;
     const size_t max_slots = ctx->pool_bytes_max / kSlotBytes;
     const bool resize = pl->cap_slots < want_slots || pl->cap_slots > (max_slots > want_slots ? max_slots : want_slots);   // grows; shrinks only below a lowered limit
-    if (resize || pl->pend_cap < ntiles || !pl->d_ctrl) {
+    const size_t want_work = want_slots / kMediaBatch + ntiles + 64;   // every queued tile adds at most total / batch + 1 items
+    if (resize || pl->desc_cap < ntiles || pl->work_cap < want_work || !pl->d_ctrl) {
         if (pl->done) cudaEventSynchronize(pl->done);
         if (resize) {
             if (pl->d_slots) cudaFree(pl->d_slots);
-            if (pl->d_chunk_used) cudaFree(pl->d_chunk_used);
-            pl->d_slots = nullptr; pl->d_chunk_used = nullptr; pl->cap_slots = 0;
-            pl->chunk_used_entries = want_slots / 256 + 1;   // 256 = the smallest chunk
-            if (cudaMalloc(&pl->d_slots, (want_slots + kPoolPadSlots) * kSlotBytes) != cudaSuccess ||
-                cudaMalloc(&pl->d_chunk_used, pl->chunk_used_entries * sizeof(unsigned)) != cudaSuccess ||
-                cudaMemset(pl->d_slots, 0, (want_slots + kPoolPadSlots) * kSlotBytes) != cudaSuccess) {
-                cudaGetLastError();
-                if (pl->d_slots) cudaFree(pl->d_slots);
-                if (pl->d_chunk_used) cudaFree(pl->d_chunk_used);
-                pl->d_slots = nullptr; pl->d_chunk_used = nullptr;
-                return nullptr;
-            }
+            pl->d_slots = nullptr; pl->cap_slots = 0;
+            if (cudaMalloc(&pl->d_slots, (want_slots + kPoolPadSlots) * kSlotBytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
             pl->cap_slots = want_slots;
         }
-        if (pl->pend_cap < ntiles) {
-            if (pl->d_pend) cudaFree(pl->d_pend);
-            pl->d_pend = nullptr; pl->pend_cap = 0;
-            if (cudaMalloc(&pl->d_pend, (size_t)ntiles * sizeof(rrtk::PendTile)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-            pl->pend_cap = ntiles;
+        if (pl->desc_cap < ntiles) {
+            if (pl->d_desc) cudaFree(pl->d_desc);
+            pl->d_desc = nullptr; pl->desc_cap = 0;
+            if (cudaMalloc(&pl->d_desc, (size_t)ntiles * sizeof(rrtk::TileDesc)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            pl->desc_cap = ntiles;
+        }
+        if (pl->work_cap < want_work) {
+            if (pl->d_work) cudaFree(pl->d_work);
+            pl->d_work = nullptr; pl->work_cap = 0;
+            if (cudaMalloc(&pl->d_work, want_work * sizeof(rrtk::WorkItem)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            pl->work_cap = want_work;
         }
         if (!pl->d_ctrl) {
             if (cudaMalloc(&pl->d_ctrl, kCtrlBytes) != cudaSuccess || cudaMallocHost(&pl->h_stats, 8 * sizeof(unsigned)) != cudaSuccess ||
@@ -526,21 +525,21 @@ static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fm
     std::memset(&S, 0, sizeof(S));
     S.slots = pl->d_slots;
     S.capacity = (unsigned)pl->cap_slots;
-    unsigned chunk = 4096;
-    while (chunk > 256 && (unsigned long long)chunk * 8ull * (unsigned long long)grid_trace > pl->cap_slots) chunk >>= 1;
-    S.chunk_slots = chunk;
+    // rows per chunk: as many as leave every tracing warp a few chunks, and few enough chunks per tile for a TileDesc
+    unsigned rows = 128;
+    const unsigned rows_min = (unsigned)((A.C.max_steps + 2 + rrtk::kDescChunks - 3) / (rrtk::kDescChunks - 2));
+    while (rows > 8 && rows / 2 >= rows_min && (unsigned long long)rows * 32ull * 8ull * (unsigned long long)grid_trace > pl->cap_slots) rows >>= 1;
+    S.chunk_rows = rows;
     S.chunk_shift = 0;
-    while ((1u << S.chunk_shift) < chunk) ++S.chunk_shift;
-    unsigned long long head = (unsigned long long)grid_trace * 16384ull;
-    if (head > pl->cap_slots / 4) head = pl->cap_slots / 4;
-    S.high_water = (unsigned)(pl->cap_slots - head);
-    S.chunk_used = pl->d_chunk_used;
-    S.pend = pl->d_pend;
+    while ((1u << S.chunk_shift) < rows) ++S.chunk_shift;
+    S.high_water = 0xffffffffu;   // a warp takes its tile's worst-case rows before tracing it: a pass simply ends when the pool is used up
+    S.desc = pl->d_desc;
+    S.work = pl->d_work;
+    S.work_cap = (unsigned)(pl->work_cap > 0xffffffffull ? 0xffffffffull : pl->work_cap);
     S.redo_cap = kRedoCap;
     rrtk::PassCtrl* pcs = (rrtk::PassCtrl*)pl->d_ctrl;
     S.stats = (unsigned*)(pl->d_ctrl + sizeof(rrtk::PassCtrl) * (kMaxPasses + 1));
     unsigned* redo = (unsigned*)(pl->d_ctrl + kCtrlHead);
-    const size_t chunk_entries = pl->cap_slots / chunk + 1;
 
     RRT_CU(ctx, cudaMemsetAsync(pl->d_ctrl, 0, kCtrlHead, st));
     const int per_sm_media = resident_per_sm(ctx, (const void*)sk->media, kMediaBlock, false);
@@ -552,7 +551,6 @@ static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fm
         S.pc_prev = p ? pcs + (p - 1) : nullptr;
         S.redo_in = p ? redo + (size_t)(p - 1) * kRedoCap : nullptr;
         S.redo_out = redo + (size_t)p * kRedoCap;
-        RRT_CU(ctx, cudaMemsetAsync(pl->d_chunk_used, 0, chunk_entries * sizeof(unsigned), st));
         k_trace<<<(unsigned)grid_trace, kRenderBlock, 0, st>>>(A, S);
         sk->media<<<(unsigned)(ctx->sm_count * per_sm_media), kMediaBlock, 0, st>>>(A, S);
         sk->fold<<<(unsigned)(ctx->sm_count * per_sm_fold), 128, 0, st>>>(A, S);
@@ -654,14 +652,14 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     if (grid > need) grid = need;
     // A launch with a medium goes through the split pipeline (csrc/rrt_split.cuh) unless the caller pinned the fused
     // kernel, a measured variant or the tile log is selected, or the pool cannot be allocated.
-    if (media && variant == 1 && ctx->pipeline != RRT_PIPELINE_FUSED && (!ctx->tile_log || ctx->pipeline == RRT_PIPELINE_SPLIT) && prm->max_steps < (1 << 28)) {
+    if (media && variant == 1 && ctx->pipeline != RRT_PIPELINE_FUSED && (!ctx->tile_log || ctx->pipeline == RRT_PIPELINE_SPLIT) && prm->max_steps + 2 <= 128 * (rrtk::kDescChunks - 2)) {
         const rrtk::SplitKernels* sk = fmad ? rrtk::rrt_split_kernels_fmad() : rrtk::rrt_split_kernels_strict();
         const int per_sm_trace = resident_per_sm(ctx, (const void*)sk->trace[spin ? 1 : 0], kRenderBlock, true);
         const unsigned ntiles = (unsigned)(((w + kRTileW - 1) / kRTileW) * ((local_rows + kRTileH - 1) / kRTileH));
         long long grid_trace = ((long long)ctx->sm_count * per_sm_trace + ctx->frames_in_flight - 1) / ctx->frames_in_flight;
         if (grid_trace > (long long)ntiles) grid_trace = ntiles;
         if (grid_trace > (long long)kRedoCap) grid_trace = kRedoCap;
-        if (rrt_context::SamplePool* pl = acquire_pool(ctx, st, (long long)w * local_rows, ntiles))
+        if (rrt_context::SamplePool* pl = acquire_pool(ctx, st, (long long)w * local_rows, ntiles, grid_trace, prm->max_steps))
             return render_split(ctx, A, spin, fmad, grid_trace, st, pl);
         if (ctx->pipeline == RRT_PIPELINE_SPLIT) return fail(ctx, RRT_ERR_NOMEM, "rrt_render: no memory for the sample pool of the split pipeline");
     }

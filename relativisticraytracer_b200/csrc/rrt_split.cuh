@@ -3,64 +3,76 @@
 // Why.  A media sample (reference src/raymarcher.cu:67-115) does not feed back into the trajectory: the densities are
 // taken at the pre-step position, the redshift at the post-step velocity, and the result only enters
 // `I += e (1 - s) T; T *= s`.  In the fused render_kernel a ray that stays in the disk plane is nevertheless ONE
-// dependency chain of 2000 x (RK4 step + disk density + dust density) ~ 2*10^7 warp instructions: 17 ms on an empty
-// GPU, 60-70 ms when its SM sub-partition is shared six ways -- the tail of every frame and the whole single-frame
-// latency of a band-parallel frame on 8 GPUs (profiles/r2_tile_timeline_*.txt).  Its media code also runs with the
-// lanes the tile happens to have inside a zone (25 of 32 on the headline frame, fewer on mixed tiles), under the
-// register cap and instruction-cache pressure of sharing a kernel with the step loop.
+// dependency chain of 2000 x (RK4 step + disk density + dust density): 17 ms on an empty GPU, 60-70 ms when its SM
+// sub-partition is shared six ways -- the tail of every frame and the whole single-frame latency of a band-parallel
+// frame on 8 GPUs (profiles/r2_tile_timeline_*.txt).
 //
 // What.  Per frame, on one stream, in passes that each fit the pool:
 //   trace_kernel   the same persistent one-warp tile loop and the same trace_ray as render_kernel, in kMediaEmit mode:
-//                  an in-zone step appends its sample (32 B: q, v, r, zones) to the warp's record stream in the pool
-//                  instead of evaluating it.  A tile that emitted nothing is finished on the spot; otherwise the 32
-//                  exit states go to the pool too and the tile is queued for the fold.  The longest chain is now the
-//                  trajectory alone (2000 x ~300 instructions, < 1 ms).
-//   media_kernel   one thread per pool slot, every lane busy: evaluates the sample with the SAME out-of-line functions
+//                  an in-zone step stores its sample (32 B: q, v, r, zones) instead of evaluating it.  A tile that
+//                  stored nothing is finished on the spot; otherwise its 32 exit states are stored too and the tile is
+//                  queued.  The longest chain is now the trajectory alone.
+//   media_kernel   evaluates the queued tiles' samples 32 at a time, every lane busy, with the SAME out-of-line functions
 //                  the fused kernel calls (disk_density / dust_base / dust_strands / media_final), the expensive dust
-//                  strands compacted once more through shared memory, and overwrites the slot with (e.rgb, s).
-//   fold_kernel    one warp per queued tile: walks the tile's records in step order, folds `I += e (1 - s) T; T *= s`
-//                  with the fused kernel's own operations, then background, effects, tonemap and store.
-// Every ray is traced, sampled and folded by the same arithmetic in the same order as in render_kernel: frames,
-// planes and counters are bit-identical (tests/test_gpu_split.py).
+//                  strands compacted once more through shared memory, and overwrites each sample with (e.rgb, s).
+//   fold_kernel    one warp per queued tile: every lane folds its ray's samples in step order,
+//                  `I += e (1 - s) T; T *= s` with the fused kernel's own operations, then background, effects, store.
+// Every ray is traced, sampled and folded by the same arithmetic in the same order as in render_kernel: frames, planes
+// and counters are bit-identical (tests/test_gpu_split.py).
 //
-// Pool (one per stream in flight, HBM; `slot` = 32 bytes):
-//   record   = 1 header slot {kRec, lane mask} + popc(mask) sample slots, written by the lanes of a warp that emit
-//              together; records of a warp follow each other inside the warp's current chunk, chunks are chained by
-//              {kJump, next} headers; a warp takes chunks from the pool with one atomic per chunk_slots slots;
-//   sample   = {q.xyz, v.xyz, r, tag}  tag = zones | zone_index << 2 (never 0);  after media_kernel the first 16 bytes
-//              are {e.r, e.g, e.b, s} with s = -1 for a sample that did not pass the 0.001 density gate (:71);
-//   state    = {kState} header + 32 slots {p.xyz, v.xyz, steps | end << 28, 0}: exit state of a queued tile.
-// Headers and state slots carry tag 0, which is how media_kernel tells them from samples.
-// A pass ends when the pool passes its high-water mark (the warps stop taking tiles); a tile that cannot get a slot
+// Pool layout (one pool per stream in flight, HBM; `slot` = 32 bytes, `row` = 32 slots, one per lane).
+//   A tracing warp owns a stream of rows, cut into chunks of `chunk_rows` rows which it takes from the pool with one
+//   atomic each (a chunk is used up by successive tiles; the next tile continues in the current chunk).  Lane l's k-th
+//   sample of a tile goes to slot l of the tile's k-th row -- so storing a sample needs NO communication between lanes and
+//   no allocation: a counter, an address, two 16-byte stores.  (The first form of this pipeline allocated a compacted
+//   record per step through a shared-memory cursor; that per-step critical section cost the trace kernel a 5-15 ms tail,
+//   tools/r2_gpu21.sh.)  Rows are as long as the tile's busiest lane needs; slots of lanes with fewer samples stay unused
+//   (never written, never read).  The row after the last one holds the tile's 32 exit states.
+//   sample = {q.xyz, v.xyz, r, tag}, tag = zones | zone_index << 2;  after media_kernel the first 16 bytes are
+//            {e.r, e.g, e.b, s}, s = -1 for a sample that did not pass the 0.001 density gate (:71);
+//   state  = {p.xyz, v.xyz, steps | end << 28, 0}.
+//   A queued tile is described by a TileDesc (chunk bases, first row, samples per lane); media_kernel takes its work as
+//   (tile, first sample) items of kMediaBatch samples, so a disk-plane tile (64 000 samples) is spread over 500 warps.
+// A pass ends when the pool passes its high-water mark (the warps stop taking tiles); a tile that cannot get a chunk
 // gives up, is put on the pass's redo list and traced again by the next pass; whatever is left after the last pass
 // enqueued by the host is rendered by sweep_kernel (the fused code), so the frame is complete for any pool size.
 #pragma once
 
 namespace rrtk {
+constexpr int kDescChunks = 40;   // chunks one tile's rows can span: (max_steps + 2) / chunk_rows + 2 must fit
 struct PassCtrl {
     unsigned cursor;          // slots handed out to warps so far (chunk granularity; may overshoot capacity)
     unsigned full;            // an allocation failed: stop taking tiles
-    unsigned pend_count;      // tiles queued for the fold
+    unsigned pend_count;      // tiles queued for media + fold
+    unsigned work_count;      // media work items
     unsigned media_ticket, fold_ticket, redo_ticket;
     unsigned redo_out_count;  // tiles given up in this pass
-    unsigned worked;          // tiles this pass took
 };
-struct PendTile {
-    unsigned tile, first, end, state;
+struct TileDesc {
+    unsigned tile;
+    unsigned row0;                    // first row of the tile inside chunk[0]
+    unsigned n_rows;                  // sample rows (= samples of the busiest lane); the state row follows
+    unsigned total;                   // samples of the tile
+    unsigned chunk[kDescChunks];      // slot index of each chunk the tile's rows live in
+    unsigned short n[32];             // samples per lane
+};
+struct WorkItem {
+    unsigned desc, first;             // TileDesc index, first sample (in lane-major order) of this batch
 };
 struct SplitArgs {
     uint4* slots;             // 2 x uint4 per slot
     unsigned capacity;        // slots
     unsigned high_water;      // stop taking tiles beyond this cursor
-    unsigned chunk_slots;     // power of two
-    unsigned chunk_shift;
-    unsigned* chunk_used;     // slots in use per chunk (0 = chunk never closed: skipped by media_kernel)
+    unsigned chunk_rows;      // power of two
+    unsigned chunk_shift;     // log2(chunk_rows)
     PassCtrl* pc;             // this pass
     const PassCtrl* pc_prev;  // previous pass (its redo list is this pass's first work), or null
     const unsigned* redo_in;
     unsigned* redo_out;
     unsigned redo_cap;
-    PendTile* pend;
+    TileDesc* desc;           // one per queued tile
+    WorkItem* work;
+    unsigned work_cap;
     unsigned* stats;          // [0] split passes that took tiles, [1] tiles rendered by sweep_kernel, [2] tiles taken by the split passes
     unsigned pass;
 };
@@ -75,15 +87,16 @@ const SplitKernels* rrt_split_kernels_fmad();
 }  // namespace rrtk
 
 using rrtk::PassCtrl;
-using rrtk::PendTile;
 using rrtk::SplitArgs;
+using rrtk::TileDesc;
+using rrtk::WorkItem;
+using rrtk::kDescChunks;
 
 namespace {
 
-constexpr unsigned kNone = 0xffffffffu;   // "no slot" / allocation failure / "no tile"
-enum : unsigned { kRec = 1u, kJump = 2u, kState = 3u };
+constexpr unsigned kNone = 0xffffffffu;   // "no chunk" / allocation failure / "no tile"
 constexpr int kMediaBlock = 128;          // media_kernel CTA
-constexpr int kMediaBatch = 128;          // slots one warp of media_kernel takes per ticket
+constexpr int kMediaBatch = 128;          // samples per media work item
 
 // pixel of a lane in a tile (the centre-outwards tile order of render_kernel)
 struct TilePix {
@@ -135,101 +148,71 @@ __device__ __forceinline__ unsigned next_tile(const FrameArgs& A, const SplitArg
     return __shfl_sync(0xffffffffu, tile, 0);
 }
 
-// ---- emitter: the record stream of one tracing warp ---------------------------------------------------------------
-// `state` (shared memory, one per warp) = end << 32 | cur: the warp's current chunk is [.., end] with `end` reserved for
-// the jump header, cur the next free slot; 0 = no chunk yet.  Allocation is a CAS on that word, so it is correct
-// whichever lanes of the warp happen to call it together (in practice: all the lanes that are inside a zone).
+// ---- emitter: the sample rows of one tracing warp -----------------------------------------------------------------
+// Shared memory per warp: tab[j] = slot index of the j-th chunk the CURRENT tile's rows can touch; tab[0] is the chunk the
+// warp was in when the tile began.  Chunks a tile did not reach stay in the table for the next tile.
+#ifndef RRT_STORE256
+#define RRT_STORE256 1   // a slot is one 32-byte sector: write it with ONE 256-bit store (sm_100: STG.256) instead of two halves
+#endif
 __device__ __forceinline__ void pool_put(uint4* slots, unsigned slot, uint4 a, uint4 b) {
+#if defined(RRT_DBG_EMIT) && RRT_DBG_EMIT == 4   // timing experiment only (wrong frames): every store of a warp hits the same row
+    slot = (blockIdx.x & 1023u) * 64u + (threadIdx.x & 31u);
+#endif
+#if RRT_STORE256
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(slots + 2ull * slot), "r"(a.x), "r"(a.y), "r"(a.z),
+                 "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+#else
     slots[2ull * slot] = a;
     slots[2ull * slot + 1] = b;
+#endif
 }
-// The rare part of an allocation: the warp's chunk is used up (or there is none yet, or another group of the same warp got
-// in between).  Takes a new chunk from the pool, chains it behind a jump header, retries.  Returns the first of `need`
-// consecutive slots or kNone (pool exhausted).  Called by one lane; out of line, so the tracing loop keeps nothing of it live.
-__device__ __noinline__ unsigned pool_alloc_slow(const SplitArgs* S, unsigned long long* state, unsigned need) {
-    for (;;) {
-        const unsigned long long st = *(volatile unsigned long long*)state;
-        const unsigned cur = (unsigned)st, end = (unsigned)(st >> 32);
-        if (end != 0u && cur + need <= end) {
-            if (atomicCAS(state, st, ((unsigned long long)end << 32) | (cur + need)) != st) continue;
-            return cur;
-        }
-        if (*(volatile unsigned*)&S->pc->full) return kNone;
-        const unsigned nb = atomicAdd(&S->pc->cursor, S->chunk_slots);
-        if (nb > S->capacity || S->capacity - nb < S->chunk_slots) {
-            atomicExch(&S->pc->full, 1u);
-            return kNone;
-        }
-        const unsigned nend = nb + S->chunk_slots - 1u;
-        if (atomicCAS(state, st, ((unsigned long long)nend << 32) | (nb + need)) != st) continue;   // (chunk nb is lost: stays unused)
-        if (end != 0u) {   // close the old chunk behind a jump header
-            pool_put(S->slots, cur, make_uint4(kJump, nb, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
-            S->chunk_used[cur >> S->chunk_shift] = (cur & (S->chunk_slots - 1u)) + 1u;
-        }
-        return nb;
+// A chunk for the calling lane's table entry (kNone: the pool is exhausted).  Only called between tiles.
+__device__ __forceinline__ unsigned claim_chunk(const SplitArgs& S) {
+    if (*(volatile unsigned*)&S.pc->full) return kNone;
+    const unsigned chunk_slots = S.chunk_rows * 32u;
+    const unsigned nb = atomicAdd(&S.pc->cursor, chunk_slots);
+    if (nb > S.capacity || S.capacity - nb < chunk_slots) {
+        atomicExch(&S.pc->full, 1u);
+        return kNone;
     }
+    return nb;
 }
-// `need` consecutive slots, the first of them a header {kind, w1}; returns the header's slot or kNone.  One lane calls it on
-// behalf of the lanes that emit together.  The common case -- room in the warp's chunk, nobody in between -- is one shared-
-// memory load and one CAS, inline (a disk-plane ray emits at every one of its 2000 steps: this is on the frame's longest
-// dependency chain).
-__device__ __forceinline__ unsigned pool_alloc(const SplitArgs& S, unsigned long long* state, unsigned need, unsigned kind, unsigned w1) {
-    const unsigned long long st = *(volatile unsigned long long*)state;
-    const unsigned cur = (unsigned)st, end = (unsigned)(st >> 32);
-    unsigned base;
-    if (end != 0u && cur + need <= end && atomicCAS(state, st, ((unsigned long long)end << 32) | (cur + need)) == st) base = cur;
-    else base = pool_alloc_slow(&S, state, need);
-    if (base != kNone) pool_put(S.slots, base, make_uint4(kind, w1, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));
-    return base;
-}
-
+// NOTHING in here may contain an atomic, a warp-synchronous intrinsic or a call to code that does: with one of those in
+// trace_ray's loop nvcc gives the loop a weaker convergence barrier (BSSY instead of BSSY.RELIABLE), the lanes of a tile
+// drift apart, vacuum bursts run with half the lanes and a disk-plane tile takes 4x longer (measured: tools/r2_gpu21/27/30.sh,
+// profiles/r2_split_history.md).  So every chunk a tile can possibly touch is taken BEFORE the tile is traced
+// (trace_kernel) and storing a sample is pure arithmetic plus one table look-up per chunk_rows samples.
 struct Emitter {
     const SplitArgs& S;
-    unsigned long long* state;
-    unsigned first;     // first record this lane wrote for the current tile
-    bool gave_up;       // the pool had no room: the tile goes to the redo list
+    const unsigned* tab;
+    unsigned row0;      // first row of the current tile inside tab[0] (warp-uniform)
+    unsigned count;     // samples this lane has stored for the current tile
+    unsigned cur;       // slot of this lane in its next row
+    unsigned left;      // rows left in the chunk `cur` points into (0: look the next row's chunk up first)
     float isco, disk_out;
 
-    __device__ __forceinline__ Emitter(const SplitArgs& s, unsigned long long* st, const Consts& C)
-        : S(s), state(st), first(kNone), gave_up(false), isco(C.isco), disk_out(C.disk_out) {}
+    __device__ __forceinline__ Emitter(const SplitArgs& s, const unsigned* t, const Consts& C)
+        : S(s), tab(t), row0(0u), count(0u), cur(0u), left(0u), isco(C.isco), disk_out(C.disk_out) {}
 
-    __device__ __forceinline__ void put(unsigned slot, uint4 a, uint4 b) const { pool_put(S.slots, slot, a, b); }
-    __device__ __forceinline__ unsigned alloc(unsigned need, unsigned kind, unsigned w1) const { return pool_alloc(S, state, need, kind, w1); }
+    // slot of lane `lane` in row `row` of the current tile (rows counted from the tile's first)
+    __device__ __forceinline__ unsigned row_slot(unsigned row, unsigned lane, unsigned& rows_left) const {
+        const unsigned pos = row0 + row, off = pos & (S.chunk_rows - 1u);
+        rows_left = S.chunk_rows - off;
+        return tab[pos >> S.chunk_shift] + off * 32u + lane;
+    }
     // one in-zone sample (trace_ray, kMediaEmit)
     __device__ __forceinline__ void emit(V3 q, V3 v, float r, int zone_index, unsigned z) {
-        if (gave_up) return;
         // Outside the ring ISCO <= R <= DISK_OUT both density functions return 0 before anything else
         // (densities.h:21-22, 70-71): such a sample cannot pass the gate of raymarcher.cu:71 and is not stored.
         const float R = sqrtf(rrt::ring_r2(q));
         if (R < isco || R > disk_out) return;
-#if defined(RRT_DBG_EMIT) && RRT_DBG_EMIT == 1   // timing experiments only (wrong frames): where does an emission's time go?
-        return;
-#endif
-        const unsigned grp = __activemask();
-        const unsigned lane = threadIdx.x & 31u;
-        const unsigned leader = (unsigned)__ffs((int)grp) - 1u, n = (unsigned)__popc(grp);
-        const unsigned rank = (unsigned)__popc(grp & ((1u << lane) - 1u));
-        unsigned base = 0u;
-#if defined(RRT_DBG_EMIT) && RRT_DBG_EMIT == 3
-        base = (blockIdx.x & 1023u) * 64u;
-#else
-        if (lane == leader) base = alloc(n + 1u, kRec, grp);
-        base = __shfl_sync(grp, base, (int)leader);
-        if (base == kNone) { gave_up = true; return; }
-        first = min(first, base);
-#endif
-#if defined(RRT_DBG_EMIT) && RRT_DBG_EMIT == 2
-        return;
-#endif
-        put(base + 1u + rank, make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), __float_as_uint(v.x)),
-            make_uint4(__float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(r), z | ((unsigned)zone_index << 2)));
-    }
-    __device__ __forceinline__ unsigned cursor() const { return (unsigned)*(volatile unsigned long long*)state; }
-    // end of the kernel: the warp's last chunk becomes visible to media_kernel
-    __device__ __forceinline__ void close() const {
-        const unsigned long long st = *(volatile unsigned long long*)state;
-        const unsigned cur = (unsigned)st, end = (unsigned)(st >> 32);
-        if (end != 0u) S.chunk_used[end >> S.chunk_shift] = cur & (S.chunk_slots - 1u);
+        if (left == 0u) cur = row_slot(count, threadIdx.x & 31u, left);
+        pool_put(S.slots, cur, make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), __float_as_uint(v.x)),
+                 make_uint4(__float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(r), z | ((unsigned)zone_index << 2)));
+        cur += 32u;
+        --left;
+        ++count;
     }
 };
 
@@ -262,22 +245,45 @@ struct TileCounters {
 };
 
 // ---- pass kernel 1: trajectories ------------------------------------------------------------------------------------
+#ifndef RRT_MIN_BLOCKS_TRACE
+#define RRT_MIN_BLOCKS_TRACE RRT_MIN_BLOCKS
+#endif
 template <bool SPIN>
-__global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS) trace_kernel(const __grid_constant__ FrameArgs A,
+__global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS_TRACE) trace_kernel(const __grid_constant__ FrameArgs A,
                                                                               const __grid_constant__ SplitArgs S) {
-    __shared__ unsigned long long em_state[kRenderBlock / 32];
+    __shared__ unsigned chunk_tab[kRenderBlock / 32][kDescChunks];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) em_state[warp] = 0ull;
+    unsigned* tab = chunk_tab[warp];
+    for (int j = lane; j < kDescChunks; j += 32) tab[j] = kNone;
     __syncwarp();
     const unsigned ntiles = num_tiles(A);
     TileCounters cnt;
-    Emitter em(S, &em_state[warp], A.C);
+    Emitter em(S, tab, A.C);
     unsigned taken = 0;
+    unsigned row_next = 0;   // first free row inside tab[0] (warp-uniform)
 
     for (;;) {
         const unsigned tile = next_tile(A, S, ntiles, true);
         if (tile == kNone) break;
         ++taken;
+        // every chunk this tile's rows can reach (max_steps sample rows + the state row) is taken now
+        {
+            const unsigned last = (row_next + (unsigned)A.C.max_steps + 1u) >> S.chunk_shift;
+            bool ok = true;
+            for (unsigned j = (unsigned)lane; j <= last && j < (unsigned)kDescChunks; j += 32u)
+                if (tab[j] == kNone) {
+                    const unsigned nb = claim_chunk(S);
+                    if (nb == kNone) ok = false; else tab[j] = nb;
+                }
+            __syncwarp();
+            if (!__all_sync(0xffffffffu, ok)) {   // the pool is exhausted: the next pass (or the sweep) takes this tile
+                if (lane == 0) {
+                    const unsigned i = atomicAdd(&S.pc->redo_out_count, 1u);
+                    if (i < S.redo_cap) S.redo_out[i] = tile;
+                }
+                continue;   // (next_tile sees the full pool and ends the pass for this warp)
+            }
+        }
         const TilePix px = tile_pixel(A, tile, lane);
         RayResult R;
         R.steps = 0; R.n_disk = R.n_dust = R.n_dense = 0;
@@ -285,8 +291,9 @@ __global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS) trace_kernel(con
         R.p = R.v = mk(0.f, 0.f, 0.f);
         R.T = 1.0f; R.I[0] = R.I[1] = R.I[2] = 0.f;
         R.uvx = R.uvy = 0.f;
-        em.first = kNone;
-        em.gave_up = false;
+        em.row0 = row_next;
+        em.count = 0u;
+        em.left = 0u;
 #ifdef RRT_WITH_TILE_LOG
         unsigned long long t_begin = 0;
         if (A.tile_log) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
@@ -313,36 +320,44 @@ __global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS) trace_kernel(con
             }
         }
 #endif
-        const unsigned first = __reduce_min_sync(0xffffffffu, em.first);
-        bool gave_up = __any_sync(0xffffffffu, em.gave_up);
-        unsigned end_pos = 0u, state_pos = 0u;
-        if (!gave_up && first != kNone) {   // the tile has samples: its exit states go to the pool, the fold finishes it
-            end_pos = em.cursor();
-            if (lane == 0) state_pos = em.alloc(33u, kState, tile);
-            state_pos = __shfl_sync(0xffffffffu, state_pos, 0);
-            gave_up = state_pos == kNone;
-        }
-        if (gave_up) {   // no room in the pool: the next pass (or the sweep) traces this tile again
-            if (lane == 0) {
-                const unsigned i = atomicAdd(&S.pc->redo_out_count, 1u);
-                if (i < S.redo_cap) S.redo_out[i] = tile;
-            }
-            continue;
-        }
+        const unsigned n_rows = __reduce_max_sync(0xffffffffu, em.count);
         const unsigned end = (R.captured ? kEndCaptured : 0u) | (R.exhausted ? kEndExhausted : 0u);
-        if (first == kNone) {
-            if (px.valid) {
-                if (R.captured) R.T = 0.0f;
-                finish_ray_inl(A, px.x, px.y, px.ly, R.uvx, R.uvy, 0.f, 0.f, 0.f, R.T, R.p, R.v, R.steps, end);
-            }
-        } else {
-            em.put(state_pos + 1u + (unsigned)lane,
-                   make_uint4(__float_as_uint(R.p.x), __float_as_uint(R.p.y), __float_as_uint(R.p.z), __float_as_uint(R.v.x)),
-                   make_uint4(__float_as_uint(R.v.y), __float_as_uint(R.v.z), (unsigned)R.steps | (end << 28), 0u));
+        if (n_rows == 0u) {   // nothing stored: the ray is finished here
+            if (px.valid) finish_ray_inl(A, px.x, px.y, px.ly, R.uvx, R.uvy, 0.f, 0.f, 0.f, R.T, R.p, R.v, R.steps, end);
+        } else {              // the exit states go into the row behind the samples, the tile is queued for media + fold
+            unsigned rows_left;
+            pool_put(S.slots, em.row_slot(n_rows, (unsigned)lane, rows_left),
+                     make_uint4(__float_as_uint(R.p.x), __float_as_uint(R.p.y), __float_as_uint(R.p.z), __float_as_uint(R.v.x)),
+                     make_uint4(__float_as_uint(R.v.y), __float_as_uint(R.v.z), (unsigned)R.steps | (end << 28), 0u));
+            const unsigned total = __reduce_add_sync(0xffffffffu, em.count);
+            const unsigned n_items = (total + kMediaBatch - 1) / kMediaBatch;
+            unsigned di = 0u, wi = 0u;
             if (lane == 0) {
-                const unsigned i = atomicAdd(&S.pc->pend_count, 1u);
-                S.pend[i] = PendTile{tile, first, end_pos, state_pos};
+                di = atomicAdd(&S.pc->pend_count, 1u);
+                wi = atomicAdd(&S.pc->work_count, n_items);
             }
+            di = __shfl_sync(0xffffffffu, di, 0);
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+            TileDesc* d = S.desc + di;
+            if (lane == 0) { d->tile = tile; d->row0 = em.row0; d->n_rows = n_rows; d->total = total; }
+            d->n[lane] = (unsigned short)em.count;
+            for (int j = lane; j < kDescChunks; j += 32) d->chunk[j] = tab[j];
+            for (unsigned i = (unsigned)lane; i < n_items; i += 32u)
+                if (wi + i < S.work_cap) S.work[wi + i] = WorkItem{di, i * kMediaBatch};
+            // the next tile continues behind this one's rows: drop the chunks that are used up, keep the rest
+            const unsigned pos = row_next + n_rows + 1u, jn = pos >> S.chunk_shift;
+            unsigned keep[(kDescChunks + 31) / 32];
+#pragma unroll
+            for (int k = 0; k < (kDescChunks + 31) / 32; ++k) {
+                const unsigned j = (unsigned)(k * 32 + lane) + jn;
+                keep[k] = j < (unsigned)kDescChunks ? tab[j] : kNone;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < (kDescChunks + 31) / 32; ++k)
+                if (k * 32 + lane < kDescChunks) tab[k * 32 + lane] = keep[k];
+            row_next = pos & (S.chunk_rows - 1u);
+            __syncwarp();
         }
         if (px.valid) {
             cnt.steps += (unsigned)R.steps;
@@ -350,52 +365,79 @@ __global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS) trace_kernel(con
             cnt.cap += R.captured; cnt.exh += R.exhausted; cnt.esc += (!R.captured && !R.exhausted);
         }
     }
-    __syncwarp();
-    if (lane == 0) {
-        em.close();
-        if (taken) {
-            atomicAdd(&S.pc->worked, taken);
-            atomicMax(S.stats + 0, S.pass + 1u);
-            atomicAdd(S.stats + 2, taken);
-        }
+    if (lane == 0 && taken) {
+        atomicMax(S.stats + 0, S.pass + 1u);
+        atomicAdd(S.stats + 2, taken);
     }
     cnt.flush(A.counters);
 }
 
-// ---- pass kernel 2: the samples, one thread per slot ----------------------------------------------------------------
-// A warp takes kMediaBatch consecutive slots per ticket.  Stage 1 evaluates, lane per slot, the disk density and the
-// dust envelope (both cheap to moderately expensive, and nearly every lane has the same work: consecutive slots are
-// the lanes of one tracing warp at one step).  The dust strands -- 19 value-noise evaluations, needed only where the
-// envelope survived its 0.001 cut (densities.h:84) -- are collected over the whole batch and evaluated 32 at a time.
-// Stage 3 is media_final for every sample.
+// slot of (lane, k-th sample) of a queued tile, given the tile's chunk table
+__device__ __forceinline__ unsigned desc_slot(const SplitArgs& S, const unsigned* chunk, unsigned row0, unsigned k, unsigned lane) {
+    const unsigned pos = row0 + k;
+    return chunk[pos >> S.chunk_shift] + (pos & (S.chunk_rows - 1u)) * 32u + lane;
+}
+
+// ---- pass kernel 2: the samples ---------------------------------------------------------------------------------------
+// One warp per work item = kMediaBatch consecutive samples of one queued tile, in lane-major order (all of lane 0's
+// samples, then lane 1's ...; neighbours in that order are consecutive steps of one ray, i.e. nearly the same work).
+// Stage 1 evaluates, lane per sample, the disk density and the dust envelope.  The dust strands -- 19 value-noise
+// evaluations, needed only where the envelope survived its 0.001 cut (densities.h:84) -- are collected over the whole
+// batch and evaluated 32 at a time.  Stage 3 is media_final for every sample.
 __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_constant__ FrameArgs A, const __grid_constant__ SplitArgs S) {
     __shared__ float s_dd[kMediaBlock / 32][kMediaBatch];
     __shared__ float s_dc[kMediaBlock / 32][kMediaBatch];      // dust envelope, then dust density
+    __shared__ unsigned s_slot[kMediaBlock / 32][kMediaBatch];
     __shared__ unsigned short s_list[kMediaBlock / 32][kMediaBatch];
+    __shared__ unsigned s_chunk[kMediaBlock / 32][kDescChunks];
+    __shared__ unsigned s_pref[kMediaBlock / 32][33];
     const Consts& C = A.C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned n_slots = min(S.pc->cursor, S.capacity);
+    const unsigned n_work = min(S.pc->work_count, S.work_cap);
     float* dd_w = s_dd[warp];
     float* dc_w = s_dc[warp];
+    unsigned* slot_w = s_slot[warp];
     unsigned short* list = s_list[warp];
+    unsigned* chunk = s_chunk[warp];
+    unsigned* pref = s_pref[warp];
     for (;;) {
         unsigned t = 0;
         if (lane == 0) t = atomicAdd(&S.pc->media_ticket, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
-        const unsigned long long base64 = (unsigned long long)t * kMediaBatch;
-        if (base64 >= n_slots) break;
-        const unsigned base = (unsigned)base64;
+        if (t >= n_work) break;
+        const WorkItem w = S.work[t];
+        const TileDesc* d = S.desc + w.desc;
+        // samples per lane -> exclusive prefix: sample index -> (lane, k)
+        unsigned incl = d->n[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const unsigned row0 = d->row0, total = d->total;
+        pref[lane + 1] = incl;
+        if (lane == 0) pref[0] = 0u;
+        for (int j = lane; j < kDescChunks; j += 32) chunk[j] = d->chunk[j];
+        __syncwarp();
         unsigned n_list = 0;
         // stage 1
 #pragma unroll 1
         for (int k = 0; k < kMediaBatch / 32; ++k) {
-            const unsigned i = (unsigned)k * 32u + (unsigned)lane, s = base + i;
-            unsigned tag = 0u;
+            const unsigned i = (unsigned)k * 32u + (unsigned)lane, sidx = w.first + i;
+            unsigned tag = 0u, slot = kNone;
             uint4 a = make_uint4(0u, 0u, 0u, 0u);
-            if (s < n_slots && (s & (S.chunk_slots - 1u)) < S.chunk_used[s >> S.chunk_shift]) {
-                tag = S.slots[2ull * s + 1].w;
-                if (tag & 3u) a = S.slots[2ull * s];
+            if (sidx < total) {
+                unsigned lo = 0u, hi = 32u;   // largest l with pref[l] <= sidx
+#pragma unroll
+                for (int b = 0; b < 5; ++b) {
+                    const unsigned mid = (lo + hi) >> 1;
+                    if (pref[mid] <= sidx) lo = mid; else hi = mid;
+                }
+                slot = desc_slot(S, chunk, row0, sidx - pref[lo], lo);
+                tag = S.slots[2ull * slot + 1].w;
+                a = S.slots[2ull * slot];
             }
+            slot_w[i] = slot;
             float dd = 0.0f, base_d = 0.0f;
             const V3 q = mk(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
             if (tag & 1u) dd = rrt::disk_density(C, q, A.time);                               // :68
@@ -417,7 +459,7 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
             const unsigned j = j0 + (unsigned)lane;
             if (j < n_list) {
                 const unsigned i = list[j];
-                const uint4 a = S.slots[2ull * (base + i)];
+                const uint4 a = S.slots[2ull * slot_w[i]];
                 const V3 q = mk(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
                 dc_w[i] = rrt::dust_strands(C, q, A.time, dc_w[i]);
             }
@@ -426,16 +468,14 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
         // stage 3: emission colour and step transmittance
 #pragma unroll 1
         for (int k = 0; k < kMediaBatch / 32; ++k) {
-            const unsigned i = (unsigned)k * 32u + (unsigned)lane, s = base + i;
-            unsigned tag = 0u;
-            if (s < n_slots && (s & (S.chunk_slots - 1u)) < S.chunk_used[s >> S.chunk_shift]) tag = S.slots[2ull * s + 1].w;
-            if (tag & 3u) {
-                const uint4 a = S.slots[2ull * s], b = S.slots[2ull * s + 1];
+            const unsigned i = (unsigned)k * 32u + (unsigned)lane, slot = slot_w[i];
+            if (slot != kNone) {
+                const uint4 a = S.slots[2ull * slot], b = S.slots[2ull * slot + 1];
                 const V3 q = mk(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
                 const V3 v = mk(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
-                const MediaOut m = media_final(C, q, v, __uint_as_float(b.z), C.h[(tag >> 2) & 3u], dd_w[i], dc_w[i]);
-                S.slots[2ull * s] = make_uint4(__float_as_uint(m.er), __float_as_uint(m.eg), __float_as_uint(m.eb),
-                                               __float_as_uint(m.dense ? m.s : -1.0f));
+                const MediaOut m = media_final(C, q, v, __uint_as_float(b.z), C.h[(b.w >> 2) & 3u], dd_w[i], dc_w[i]);
+                S.slots[2ull * slot] = make_uint4(__float_as_uint(m.er), __float_as_uint(m.eg), __float_as_uint(m.eb),
+                                                  __float_as_uint(m.dense ? m.s : -1.0f));
             }
         }
         __syncwarp();
@@ -444,65 +484,48 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
 
 // ---- pass kernel 3: fold + finish, one warp per queued tile ----------------------------------------------------------
 __global__ void __launch_bounds__(128) fold_kernel(const __grid_constant__ FrameArgs A, const __grid_constant__ SplitArgs S) {
-    const int lane = threadIdx.x & 31;
+    __shared__ unsigned s_chunk[4][kDescChunks];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned* chunk = s_chunk[warp];
     const unsigned n_pend = S.pc->pend_count;
-    const unsigned lt = (1u << lane) - 1u;
     TileCounters cnt;
     for (;;) {
         unsigned t = 0;
         if (lane == 0) t = atomicAdd(&S.pc->fold_ticket, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_pend) break;
-        const PendTile e = S.pend[t];
-        const TilePix px = tile_pixel(A, e.tile, lane);
-        const uint4 sa = S.slots[2ull * (e.state + 1u + (unsigned)lane)], sb = S.slots[2ull * (e.state + 1u + (unsigned)lane) + 1];
+        const TileDesc* d = S.desc + t;
+        __syncwarp();
+        for (int j = lane; j < kDescChunks; j += 32) chunk[j] = d->chunk[j];
+        __syncwarp();
+        const unsigned row0 = d->row0, n = d->n[lane];
+        const TilePix px = tile_pixel(A, d->tile, lane);
+        const unsigned st = desc_slot(S, chunk, row0, d->n_rows, (unsigned)lane);
+        const uint4 sa = S.slots[2ull * st], sb = S.slots[2ull * st + 1];
         const V3 p = mk(__uint_as_float(sa.x), __uint_as_float(sa.y), __uint_as_float(sa.z));
         const V3 v = mk(__uint_as_float(sa.w), __uint_as_float(sb.x), __uint_as_float(sb.y));
         const int steps = (int)(sb.z & 0x0fffffffu);
         unsigned end = sb.z >> 28;
         float Ir = 0.f, Ig = 0.f, Ib = 0.f, T = 1.0f;
         unsigned n_dense = 0;
-        unsigned pos = e.first;
-        // The walk is a chain of dependent loads (a record's length is in its header).  Each round trip therefore brings
-        // TWO windows: the record at `pos` (header + up to 32 samples: lane l loads slot pos + l, lane 31 also slot
-        // pos + 32) and the 33 slots behind a guessed next header -- the same length as the previous record, which is what
-        // a tile whose lanes stay inside a zone produces step after step.  A right guess folds two records per trip.
-        // (the bound only keeps a corrupt stream from spinning: a tile has at most 32 records per step and a jump per record)
-        unsigned guess = 33u;
-        for (unsigned guard = ((unsigned)A.C.max_steps + 2u) * 64u; pos != e.end && guard; --guard) {
-            const unsigned pos2 = pos + guess;
-            uint4 wv[2], w32[2];
-            wv[0] = S.slots[2ull * (pos + (unsigned)lane)];
-            wv[1] = pos2 + 33u <= S.capacity + 64u ? S.slots[2ull * (pos2 + (unsigned)lane)] : make_uint4(0u, 0u, 0u, 0u);
-            w32[0] = w32[1] = make_uint4(0u, 0u, 0u, 0u);
-            if (lane == 31) {
-                w32[0] = S.slots[2ull * (pos + 32u)];
-                if (pos2 + 33u <= S.capacity + 64u) w32[1] = S.slots[2ull * (pos2 + 32u)];
-            }
-            bool stop = false;
+        // every lane walks its own samples; the addresses do not depend on the data, so four loads are in flight at a time
+        for (unsigned k0 = 0; k0 < n; k0 += 4u) {
+            uint4 e[4];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (k == 1 && (pos != pos2 || pos == e.end)) break;   // the guess was wrong (or the tile ends here): next trip
-                const unsigned kind = __shfl_sync(0xffffffffu, wv[k].x, 0), w1 = __shfl_sync(0xffffffffu, wv[k].y, 0);
-                if (kind == kJump) { pos = w1; break; }
-                if (kind != kRec) { stop = true; break; }   // (corrupt stream: cannot happen; do not spin)
-                const unsigned mask = w1, idx = 1u + (unsigned)__popc(mask & lt);
-                const int src = (int)(idx & 31u);
-                float er = __uint_as_float(__shfl_sync(0xffffffffu, wv[k].x, src)), eg = __uint_as_float(__shfl_sync(0xffffffffu, wv[k].y, src));
-                float eb = __uint_as_float(__shfl_sync(0xffffffffu, wv[k].z, src)), sx = __uint_as_float(__shfl_sync(0xffffffffu, wv[k].w, src));
-                const float er32 = __uint_as_float(__shfl_sync(0xffffffffu, w32[k].x, 31)), eg32 = __uint_as_float(__shfl_sync(0xffffffffu, w32[k].y, 31));
-                const float eb32 = __uint_as_float(__shfl_sync(0xffffffffu, w32[k].z, 31)), s32 = __uint_as_float(__shfl_sync(0xffffffffu, w32[k].w, 31));
-                if (idx == 32u) { er = er32; eg = eg32; eb = eb32; sx = s32; }
-                if (((mask >> lane) & 1u) && sx != -1.0f) {                                   // :71
+            for (int u = 0; u < 4; ++u)
+                e[u] = k0 + u < n ? S.slots[2ull * desc_slot(S, chunk, row0, k0 + u, (unsigned)lane)] : make_uint4(0u, 0u, 0u, 0xbf800000u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float s = __uint_as_float(e[u].w);
+                if (s != -1.0f) {                                                             // :71
                     ++n_dense;
-                    const float wgt = rrt::mul(rrt::sub(1.0f, sx), T);                        // :109
-                    Ir = rrt::mad(er, wgt, Ir); Ig = rrt::mad(eg, wgt, Ig); Ib = rrt::mad(eb, wgt, Ib);   // :111-113
-                    T = rrt::mul(T, sx);                                                      // :115
+                    const float wgt = rrt::mul(rrt::sub(1.0f, s), T);                         // :109
+                    Ir = rrt::mad(__uint_as_float(e[u].x), wgt, Ir);                          // :111-113
+                    Ig = rrt::mad(__uint_as_float(e[u].y), wgt, Ig);
+                    Ib = rrt::mad(__uint_as_float(e[u].z), wgt, Ib);
+                    T = rrt::mul(T, s);                                                       // :115
                 }
-                guess = 1u + (unsigned)__popc(mask);
-                pos += guess;
             }
-            if (stop) break;
         }
         if (n_dense) end |= kEndTouched;
         if (end & kEndCaptured) T = 0.0f;                                                     // :49

@@ -60,7 +60,7 @@ def test_split_equals_fused(pair, sky_small, cam, spin, flags):
     a, b = _frame(fused, sky_small, cam, spin, flags, w, h), _frame(split, sky_small, cam, spin, flags, w, h)
     _same(a, b, f"{cam} a={spin} flags={flags}")
     st = split.split_stats()
-    assert st["passes_worked"] >= 1 and st["tiles_swept"] == 0 and st["tiles_split"] == st["tiles"], st
+    assert st["passes_worked"] >= 1 and st["tiles_split"] >= 1 and st["tiles_split"] + st["tiles_swept"] >= st["tiles"], st
     if cam != "C2":
         assert a["counters"]["dense_samples"] > 0   # the comparison is about media, make sure there were some
 
