@@ -163,6 +163,7 @@ struct rrt_context {
     };
     SamplePool pools[RRT_HOST_SLOTS];
     unsigned long long pool_clock = 0;
+    int passes_hint = 2;                  // passes the last frame with history needed: the first guess of a pool without one
     unsigned long long launches = 0;      // kernels this context has launched for rrt_render* / rrt_assemble_bands
     std::string err;
     std::mutex mu;
@@ -513,10 +514,11 @@ static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fm
 
     // passes to enqueue: what the last completed frame on this pool needed (the sweep renders whatever a wrong guess leaves)
     const unsigned* hs = pl->h_stats;   // [0] passes that took tiles [1] tiles swept [2] tiles taken by passes [3] passes enqueued [4] ntiles
-    int passes = 2;
+    int passes = ctx->passes_hint;
     if (hs[3] != 0u) {
         if (hs[1] == 0u) passes = (int)hs[0];
         else passes = (int)(((unsigned long long)hs[3] * hs[4] + hs[2]) / (hs[2] ? hs[2] : 1u)) + 1;
+        ctx->passes_hint = passes < 1 ? 1 : passes;
     }
     if (passes < 1) passes = 1;
     if (passes > ctx->max_passes) passes = ctx->max_passes;
