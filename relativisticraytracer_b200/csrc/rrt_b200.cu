@@ -145,6 +145,7 @@ struct rrt_context {
     int frames_in_flight = 1; // render launches expected to run concurrently: each gets 1/n of the resident-CTA slots
     // split pipeline (csrc/rrt_split.cuh): trace / media / fold kernels over a sample pool, one pool per stream in flight
     int pipeline = RRT_PIPELINE_AUTO;
+    int trace_choice = 0;                 // split pipeline's tracer: 0 auto (packed f32x2 under the FMAD contract), 1 scalar, 2 packed (RRT_TRACE)
     size_t pool_bytes_max = 16ull << 30;  // per pool (RRT_POOL_MB / rrt_set_sample_pool)
     int max_passes = 32;
     struct SamplePool {
@@ -302,6 +303,7 @@ int rrt_context_create(int device, rrt_context** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* k = std::getenv("RRT_KERNEL")) ctx->kernel_choice = !std::strcmp(k, "packed") ? 2 : (!std::strcmp(k, "scalar") ? 1 : 0);
     if (const char* k = std::getenv("RRT_PIPELINE")) ctx->pipeline = !std::strcmp(k, "split") ? RRT_PIPELINE_SPLIT : (!std::strcmp(k, "fused") ? RRT_PIPELINE_FUSED : RRT_PIPELINE_AUTO);
+    if (const char* k = std::getenv("RRT_TRACE")) ctx->trace_choice = !std::strcmp(k, "packed") ? 2 : (!std::strcmp(k, "scalar") ? 1 : 0);
     if (const char* k = std::getenv("RRT_POOL_MB")) { const long long mb = std::atoll(k); if (mb > 0) ctx->pool_bytes_max = (size_t)mb << 20; }
     if (const char* k = std::getenv("RRT_MAX_PASSES")) { const int n = std::atoi(k); if (n >= 1 && n <= kMaxPasses) ctx->max_passes = n; }
 #ifdef RRT_WITH_VARIANTS
@@ -446,7 +448,7 @@ static int resident_per_sm(rrt_context* ctx, const void* kern, int block, bool m
 // The pool this stream renders through: its own if it has one, else a free one, else the least recently used one
 // (stream-ordered behind that pool's last frame).  (Re)allocated when the frame needs more than it holds.  Returns null,
 // with no error set, when the memory is not there: the caller renders fused.
-static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, long long local_pixels, unsigned ntiles, long long grid_trace, int max_steps) {
+static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, long long local_pixels, unsigned ntiles, long long grid_trace, int rows_per_tile) {
     rrt_context::SamplePool* pl = nullptr;
     for (auto& c : ctx->pools)
         if (c.in_use && c.stream == st) pl = &c;
@@ -459,8 +461,8 @@ static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, 
         if (pl->done && cudaStreamWaitEvent(st, pl->done, 0) != cudaSuccess) return nullptr;
     }
     // ~128 samples per pixel before a frame is cut into passes, plus what the tracing warps hold in reserve: each takes
-    // the rows its tile could need in the worst case (max_steps + 1 rows of 1 KiB) before it traces it
-    size_t want_bytes = (size_t)local_pixels * 4096 + (size_t)grid_trace * ((size_t)max_steps + 2 + 256) * 1024;
+    // the rows its tile could need in the worst case (max_steps + 1 rows of 1 KiB per ray of a thread) before it traces it
+    size_t want_bytes = (size_t)local_pixels * 4096 + (size_t)grid_trace * ((size_t)rows_per_tile + 256) * 1024;
     if (want_bytes < (64ull << 20)) want_bytes = 64ull << 20;
     if (want_bytes > ctx->pool_bytes_max) want_bytes = ctx->pool_bytes_max;
     size_t want_slots = want_bytes / kSlotBytes;
@@ -505,12 +507,13 @@ static rrt_context::SamplePool* acquire_pool(rrt_context* ctx, cudaStream_t st, 
 
 // One frame through trace / media / fold passes and the closing sweep.  `grid_trace` = the persistent grid of the
 // tracing kernels for this launch (already divided by the frames in flight).
-static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fmad, long long grid_trace, cudaStream_t st,
+static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fmad, bool packed_trace, long long grid_trace, cudaStream_t st,
                         rrt_context::SamplePool* pl) {
     const rrtk::SplitKernels* sk = fmad ? rrtk::rrt_split_kernels_fmad() : rrtk::rrt_split_kernels_strict();
-    auto k_trace = sk->trace[spin ? 1 : 0];
+    auto k_trace = packed_trace ? sk->trace_packed[spin ? 1 : 0] : sk->trace[spin ? 1 : 0];
     auto k_sweep = sk->sweep[spin ? 1 : 0];
-    const unsigned ntiles = (unsigned)(((A.w + kRTileW - 1) / kRTileW) * ((A.local_rows + kRTileH - 1) / kRTileH));
+    const unsigned ntiles = packed_trace ? (unsigned)(((A.w + kTile16W - 1) / kTile16W) * ((A.local_rows + kTile16H - 1) / kTile16H))
+                                         : (unsigned)(((A.w + kRTileW - 1) / kRTileW) * ((A.local_rows + kRTileH - 1) / kRTileH));
 
     // passes to enqueue: what the last completed frame on this pool needed (the sweep renders whatever a wrong guess leaves)
     const unsigned* hs = pl->h_stats;   // [0] passes that took tiles [1] tiles swept [2] tiles taken by passes [3] passes enqueued [4] ntiles
@@ -529,7 +532,7 @@ static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fm
     S.capacity = (unsigned)pl->cap_slots;
     // rows per chunk: as many as leave every tracing warp a few chunks, and few enough chunks per tile for a TileDesc
     unsigned rows = 128;
-    const unsigned rows_min = (unsigned)((A.C.max_steps + 2 + rrtk::kDescChunks - 3) / (rrtk::kDescChunks - 2));
+    const unsigned rows_min = (unsigned)(((packed_trace ? 2 : 1) * (A.C.max_steps + 1) + 1 + rrtk::kDescChunks - 3) / (rrtk::kDescChunks - 2));
     while (rows > 8 && rows / 2 >= rows_min && (unsigned long long)rows * 32ull * 8ull * (unsigned long long)grid_trace > pl->cap_slots) rows >>= 1;
     S.chunk_rows = rows;
     S.chunk_shift = 0;
@@ -539,6 +542,7 @@ static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fm
     S.work = pl->d_work;
     S.work_cap = (unsigned)(pl->work_cap > 0xffffffffull ? 0xffffffffull : pl->work_cap);
     S.redo_cap = kRedoCap;
+    S.tile16 = packed_trace ? 1u : 0u;
     rrtk::PassCtrl* pcs = (rrtk::PassCtrl*)pl->d_ctrl;
     S.stats = (unsigned*)(pl->d_ctrl + sizeof(rrtk::PassCtrl) * (kMaxPasses + 1));
     unsigned* redo = (unsigned*)(pl->d_ctrl + kCtrlHead);
@@ -656,13 +660,20 @@ int rrt_render(rrt_context* ctx, const rrt_params* prm, const rrt_camera* cam, c
     // kernel, a measured variant or the tile log is selected, or the pool cannot be allocated.
     if (media && variant == 1 && ctx->pipeline != RRT_PIPELINE_FUSED && (!ctx->tile_log || ctx->pipeline == RRT_PIPELINE_SPLIT) && prm->max_steps + 2 <= 128 * (rrtk::kDescChunks - 2)) {
         const rrtk::SplitKernels* sk = fmad ? rrtk::rrt_split_kernels_fmad() : rrtk::rrt_split_kernels_strict();
-        const int per_sm_trace = resident_per_sm(ctx, (const void*)sk->trace[spin ? 1 : 0], kRenderBlock, true);
-        const unsigned ntiles = (unsigned)(((w + kRTileW - 1) / kRTileW) * ((local_rows + kRTileH - 1) / kRTileH));
+        // the tracer: two rays per thread in packed f32x2 registers where that kernel exists (FMAD contract), else one per thread
+        const bool packed_trace = sk->trace_packed[0] != nullptr && ctx->trace_choice != 1 &&
+                                  2ll * (prm->max_steps + 1) + 2 <= 128ll * (rrtk::kDescChunks - 2);
+        auto k_trace = packed_trace ? sk->trace_packed[spin ? 1 : 0] : sk->trace[spin ? 1 : 0];
+        const int per_sm_trace = resident_per_sm(ctx, (const void*)k_trace, kRenderBlock, true);
+        const unsigned ntiles8 = (unsigned)(((w + kRTileW - 1) / kRTileW) * ((local_rows + kRTileH - 1) / kRTileH));
+        const unsigned ntiles16 = (unsigned)(((w + kTile16W - 1) / kTile16W) * ((local_rows + kTile16H - 1) / kTile16H));
+        const unsigned ntiles = packed_trace ? ntiles16 : ntiles8;
         long long grid_trace = ((long long)ctx->sm_count * per_sm_trace + ctx->frames_in_flight - 1) / ctx->frames_in_flight;
         if (grid_trace > (long long)ntiles) grid_trace = ntiles;
         if (grid_trace > (long long)kRedoCap) grid_trace = kRedoCap;
-        if (rrt_context::SamplePool* pl = acquire_pool(ctx, st, (long long)w * local_rows, ntiles, grid_trace, prm->max_steps))
-            return render_split(ctx, A, spin, fmad, grid_trace, st, pl);
+        const int rows_per_tile = (packed_trace ? 2 : 1) * (prm->max_steps + 1) + 1;
+        if (rrt_context::SamplePool* pl = acquire_pool(ctx, st, (long long)w * local_rows, packed_trace ? 2 * ntiles16 : ntiles8, grid_trace, rows_per_tile))
+            return render_split(ctx, A, spin, fmad, packed_trace, grid_trace, st, pl);
         if (ctx->pipeline == RRT_PIPELINE_SPLIT) return fail(ctx, RRT_ERR_NOMEM, "rrt_render: no memory for the sample pool of the split pipeline");
     }
     kern<<<(unsigned)grid, block, 0, st>>>(A);

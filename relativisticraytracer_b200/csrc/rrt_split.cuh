@@ -27,10 +27,11 @@
 //   no allocation: a counter, an address, two 16-byte stores.  (The first form of this pipeline allocated a compacted
 //   record per step through a shared-memory cursor; that per-step critical section cost the trace kernel a 5-15 ms tail,
 //   tools/r2_gpu21.sh.)  Rows are as long as the tile's busiest lane needs; slots of lanes with fewer samples stay unused
-//   (never written, never read).  The row after the last one holds the tile's 32 exit states.
+//   (never written, never read).  A lane that stored samples puts its ray's exit state behind its last one; a lane that
+//   stored none finishes its ray on the spot.
 //   sample = {q.xyz, v.xyz, r, tag}, tag = zones | zone_index << 2;  after media_kernel the first 16 bytes are
 //            {e.r, e.g, e.b, s}, s = -1 for a sample that did not pass the 0.001 density gate (:71);
-//   state  = {p.xyz, v.xyz, steps | end << 28, 0}.
+//   state  = {p.xyz, v.xyz, steps | end << 28, 0}, stored by each lane behind its own last sample.
 //   A queued tile is described by a TileDesc (chunk bases, first row, samples per lane); media_kernel takes its work as
 //   (tile, first sample) items of kMediaBatch samples, so a disk-plane tile (64 000 samples) is spread over 500 warps.
 // A pass ends when the pool passes its high-water mark (the warps stop taking tiles); a tile that cannot get a chunk
@@ -49,12 +50,14 @@ struct PassCtrl {
     unsigned redo_out_count;  // tiles given up in this pass
 };
 struct TileDesc {
-    unsigned tile;
-    unsigned row0;                    // first row of the tile inside chunk[0]
-    unsigned n_rows;                  // sample rows (= samples of the busiest lane); the state row follows
-    unsigned total;                   // samples of the tile
+    unsigned tile;                    // tile index (8x4 tiles, or 16x4 tiles for the packed tracer)
+    unsigned row0;                    // row of this ray group's first sample inside chunk[0]
+    unsigned stride_kind;             // row stride between a lane's consecutive samples (1, or 2 for the halves of a packed
+                                      // tile, whose rows interleave) | kind << 8: 0 an 8x4 tile, 1 / 2 the even / odd pixels
+                                      // of a 16x4 tile (trace_kernel_p)
+    unsigned total;                   // samples of the group
     unsigned chunk[kDescChunks];      // slot index of each chunk the tile's rows live in
-    unsigned short n[32];             // samples per lane
+    unsigned short n[32];             // samples per lane; lane l's exit state sits behind its last sample (its n-th row)
 };
 struct WorkItem {
     unsigned desc, first;             // TileDesc index, first sample (in lane-major order) of this batch
@@ -75,9 +78,11 @@ struct SplitArgs {
     unsigned work_cap;
     unsigned* stats;          // [0] split passes that took tiles, [1] tiles rendered by sweep_kernel, [2] tiles taken by the split passes
     unsigned pass;
+    unsigned tile16;          // tickets and redo lists count 16x4 tiles (the packed tracer) instead of 8x4 tiles
 };
 struct SplitKernels {
     void (*trace[2])(const FrameArgs, const SplitArgs);   // [spin != 0]
+    void (*trace_packed[2])(const FrameArgs, const SplitArgs);   // two rays per thread (FMAD contract only, else null)
     void (*media)(const FrameArgs, const SplitArgs);
     void (*fold)(const FrameArgs, const SplitArgs);
     void (*sweep[2])(const FrameArgs, const SplitArgs);
@@ -121,6 +126,28 @@ __device__ __forceinline__ TilePix tile_pixel(const FrameArgs& A, unsigned tile,
 }
 __device__ __forceinline__ unsigned num_tiles(const FrameArgs& A) {
     return (unsigned)(((A.w + kRTileW - 1) / kRTileW) * ((A.local_rows + kRTileH - 1) / kRTileH));
+}
+
+// the same for the packed tracer's 16x4 tiles: thread (lane & 7, lane >> 3) owns pixels (2 lx + hf, ly), hf = 0, 1
+constexpr int kTile16W = 16, kTile16H = 4;
+__device__ __forceinline__ TilePix tile_pixel16(const FrameArgs& A, unsigned tile, int lane, int hf) {
+    const int ntx = (A.w + kTile16W - 1) / kTile16W;
+    const int nty = (A.local_rows + kTile16H - 1) / kTile16H;
+    const int tx = (int)(tile % (unsigned)ntx), k = (int)(tile / (unsigned)ntx);
+    const int c = nty >> 1, m = min(c, nty - 1 - c);
+    int ty;
+    if (k <= 2 * m) ty = (k & 1) ? c + ((k + 1) >> 1) : c - (k >> 1);
+    else ty = (c > nty - 1 - c) ? (c - m - 1) - (k - (2 * m + 1)) : (c + m + 1) + (k - (2 * m + 1));
+    TilePix t;
+    t.x = tx * kTile16W + 2 * (lane & 7) + hf;
+    t.ly = ty * kTile16H + (lane >> 3);
+    const int grp = t.ly / A.band_group;
+    t.y = (grp * A.band_nranks + A.band_rank) * A.band_group + (t.ly - grp * A.band_group);
+    t.valid = t.x < A.w && t.ly < A.local_rows && t.y < A.h;
+    return t;
+}
+__device__ __forceinline__ unsigned num_tiles16(const FrameArgs& A) {
+    return (unsigned)(((A.w + kTile16W - 1) / kTile16W) * ((A.local_rows + kTile16H - 1) / kTile16H));
 }
 
 // Next tile of a pass (lane 0 decides, everyone gets it): the previous pass's redo list first, then fresh tickets.
@@ -244,6 +271,61 @@ struct TileCounters {
     }
 };
 
+// Queues one group of 32 rays (an 8x4 tile, or one half of a packed 16x4 tile) for media_kernel and fold_kernel: its
+// descriptor and its media work items.  Called by the whole warp; `count` = samples of this lane's ray.
+__device__ __forceinline__ void queue_group(const SplitArgs& S, const unsigned* tab, unsigned tile, unsigned row0, unsigned stride, unsigned kind,
+                                            unsigned count, int lane) {
+    const unsigned total = __reduce_add_sync(0xffffffffu, count);
+    const unsigned n_items = (total + kMediaBatch - 1) / kMediaBatch;
+    unsigned di = 0u, wi = 0u;
+    if (lane == 0) {
+        di = atomicAdd(&S.pc->pend_count, 1u);
+        wi = atomicAdd(&S.pc->work_count, n_items);
+    }
+    di = __shfl_sync(0xffffffffu, di, 0);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    TileDesc* d = S.desc + di;
+    if (lane == 0) { d->tile = tile; d->row0 = row0; d->stride_kind = stride | (kind << 8); d->total = total; }
+    d->n[lane] = (unsigned short)count;
+    for (int j = lane; j < kDescChunks; j += 32) d->chunk[j] = tab[j];
+    for (unsigned i = (unsigned)lane; i < n_items; i += 32u)
+        if (wi + i < S.work_cap) S.work[wi + i] = WorkItem{di, i * kMediaBatch};
+}
+// The next tile continues `used` rows further on: drop the chunks that are used up, keep the rest of the stock.
+__device__ __forceinline__ void advance_rows(const SplitArgs& S, unsigned* tab, unsigned& row_next, unsigned used, int lane) {
+    const unsigned pos = row_next + used, jn = pos >> S.chunk_shift;
+    unsigned keep[(kDescChunks + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (kDescChunks + 31) / 32; ++k) {
+        const unsigned j = (unsigned)(k * 32 + lane) + jn;
+        keep[k] = j < (unsigned)kDescChunks ? tab[j] : kNone;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < (kDescChunks + 31) / 32; ++k)
+        if (k * 32 + lane < kDescChunks) tab[k * 32 + lane] = keep[k];
+    row_next = pos & (S.chunk_rows - 1u);
+    __syncwarp();
+}
+// Before a tile is traced: every chunk its rows can reach (`rows` of them from row_next on) is taken.  False: pool used up.
+__device__ __forceinline__ bool stock_chunks(const SplitArgs& S, unsigned* tab, unsigned row_next, unsigned rows, int lane) {
+    const unsigned last = (row_next + rows) >> S.chunk_shift;
+    bool ok = true;
+    for (unsigned j = (unsigned)lane; j <= last && j < (unsigned)kDescChunks; j += 32u)
+        if (tab[j] == kNone) {
+            const unsigned nb = claim_chunk(S);
+            if (nb == kNone) ok = false; else tab[j] = nb;
+        }
+    __syncwarp();
+    return __all_sync(0xffffffffu, ok);
+}
+__device__ __forceinline__ void redo_later(const SplitArgs& S, unsigned tile, int lane) {
+    if (lane == 0) {
+        const unsigned i = atomicAdd(&S.pc->redo_out_count, 1u);
+        if (i < S.redo_cap) S.redo_out[i] = tile;
+    }
+}
+
 // ---- pass kernel 1: trajectories ------------------------------------------------------------------------------------
 #ifndef RRT_MIN_BLOCKS_TRACE
 #define RRT_MIN_BLOCKS_TRACE RRT_MIN_BLOCKS
@@ -266,23 +348,10 @@ __global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS_TRACE) trace_kern
         const unsigned tile = next_tile(A, S, ntiles, true);
         if (tile == kNone) break;
         ++taken;
-        // every chunk this tile's rows can reach (max_steps sample rows + the state row) is taken now
-        {
-            const unsigned last = (row_next + (unsigned)A.C.max_steps + 1u) >> S.chunk_shift;
-            bool ok = true;
-            for (unsigned j = (unsigned)lane; j <= last && j < (unsigned)kDescChunks; j += 32u)
-                if (tab[j] == kNone) {
-                    const unsigned nb = claim_chunk(S);
-                    if (nb == kNone) ok = false; else tab[j] = nb;
-                }
-            __syncwarp();
-            if (!__all_sync(0xffffffffu, ok)) {   // the pool is exhausted: the next pass (or the sweep) takes this tile
-                if (lane == 0) {
-                    const unsigned i = atomicAdd(&S.pc->redo_out_count, 1u);
-                    if (i < S.redo_cap) S.redo_out[i] = tile;
-                }
-                continue;   // (next_tile sees the full pool and ends the pass for this warp)
-            }
+        // every chunk this tile's rows can reach (max_steps sample rows + one for the exit states) is taken now
+        if (!stock_chunks(S, tab, row_next, (unsigned)A.C.max_steps + 1u, lane)) {
+            redo_later(S, tile, lane);   // the pool is used up: the next pass (or the sweep) takes this tile
+            continue;                    // (next_tile sees the full pool and ends the pass for this warp)
         }
         const TilePix px = tile_pixel(A, tile, lane);
         RayResult R;
@@ -322,42 +391,17 @@ __global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS_TRACE) trace_kern
 #endif
         const unsigned n_rows = __reduce_max_sync(0xffffffffu, em.count);
         const unsigned end = (R.captured ? kEndCaptured : 0u) | (R.exhausted ? kEndExhausted : 0u);
-        if (n_rows == 0u) {   // nothing stored: the ray is finished here
+        if (em.count == 0u) {   // nothing stored: this ray is finished here
             if (px.valid) finish_ray_inl(A, px.x, px.y, px.ly, R.uvx, R.uvy, 0.f, 0.f, 0.f, R.T, R.p, R.v, R.steps, end);
-        } else {              // the exit states go into the row behind the samples, the tile is queued for media + fold
+        } else {                // the exit state goes behind the ray's samples; fold_kernel finishes it
             unsigned rows_left;
-            pool_put(S.slots, em.row_slot(n_rows, (unsigned)lane, rows_left),
+            pool_put(S.slots, em.row_slot(em.count, (unsigned)lane, rows_left),
                      make_uint4(__float_as_uint(R.p.x), __float_as_uint(R.p.y), __float_as_uint(R.p.z), __float_as_uint(R.v.x)),
                      make_uint4(__float_as_uint(R.v.y), __float_as_uint(R.v.z), (unsigned)R.steps | (end << 28), 0u));
-            const unsigned total = __reduce_add_sync(0xffffffffu, em.count);
-            const unsigned n_items = (total + kMediaBatch - 1) / kMediaBatch;
-            unsigned di = 0u, wi = 0u;
-            if (lane == 0) {
-                di = atomicAdd(&S.pc->pend_count, 1u);
-                wi = atomicAdd(&S.pc->work_count, n_items);
-            }
-            di = __shfl_sync(0xffffffffu, di, 0);
-            wi = __shfl_sync(0xffffffffu, wi, 0);
-            TileDesc* d = S.desc + di;
-            if (lane == 0) { d->tile = tile; d->row0 = em.row0; d->n_rows = n_rows; d->total = total; }
-            d->n[lane] = (unsigned short)em.count;
-            for (int j = lane; j < kDescChunks; j += 32) d->chunk[j] = tab[j];
-            for (unsigned i = (unsigned)lane; i < n_items; i += 32u)
-                if (wi + i < S.work_cap) S.work[wi + i] = WorkItem{di, i * kMediaBatch};
-            // the next tile continues behind this one's rows: drop the chunks that are used up, keep the rest
-            const unsigned pos = row_next + n_rows + 1u, jn = pos >> S.chunk_shift;
-            unsigned keep[(kDescChunks + 31) / 32];
-#pragma unroll
-            for (int k = 0; k < (kDescChunks + 31) / 32; ++k) {
-                const unsigned j = (unsigned)(k * 32 + lane) + jn;
-                keep[k] = j < (unsigned)kDescChunks ? tab[j] : kNone;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < (kDescChunks + 31) / 32; ++k)
-                if (k * 32 + lane < kDescChunks) tab[k * 32 + lane] = keep[k];
-            row_next = pos & (S.chunk_rows - 1u);
-            __syncwarp();
+        }
+        if (n_rows != 0u) {     // the tile is queued for media + fold
+            queue_group(S, tab, tile, em.row0, 1u, 0u, em.count, lane);
+            advance_rows(S, tab, row_next, n_rows + 1u, lane);
         }
         if (px.valid) {
             cnt.steps += (unsigned)R.steps;
@@ -372,9 +416,255 @@ __global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS_TRACE) trace_kern
     cnt.flush(A.counters);
 }
 
+#if RRT_FMAD
+// ---- pass kernel 1, packed: trajectories with two rays per thread (rrt_packed.cuh) ------------------------------------------
+// The tracing loop of render_kernel_p (16x4-pixel tiles, thread (lx, ly) owns pixels (2 lx, ly) and (2 lx + 1, ly) as the halves
+// of f32x2 registers, warp-uniform vacuum bursts, checked iterations per half) with the media sample of an in-zone step
+// stored instead of evaluated.  The packed step is ~6 % faster than the scalar one on the FMA pipe (profiles/r2_rf_model.md) and
+// the fused packed kernel lost that to its per-half media calls; here there are none.  The rows of the two halves interleave
+// (half hf's k-th sample row is row 2 k + hf of the tile), each half is queued as its own group of 32 rays.
+struct Emitter2 {
+    const SplitArgs& S;
+    const unsigned* tab;
+    unsigned row0;
+    unsigned count[2];
+    float isco, disk_out;
+    __device__ __forceinline__ Emitter2(const SplitArgs& s, const unsigned* t, const Consts& C)
+        : S(s), tab(t), row0(0u), isco(C.isco), disk_out(C.disk_out) { count[0] = count[1] = 0u; }
+    __device__ __forceinline__ unsigned slot(int hf, unsigned k, unsigned lane) const {
+        const unsigned pos = row0 + 2u * k + (unsigned)hf;
+        return tab[pos >> S.chunk_shift] + (pos & (S.chunk_rows - 1u)) * 32u + lane;
+    }
+    __device__ __forceinline__ void emit(int hf, V3 q, V3 v, float r, int zone_index, unsigned z) {
+        const float R = sqrtf(rrt::ring_r2(q));   // see Emitter::emit
+        if (R < isco || R > disk_out) return;
+        pool_put(S.slots, slot(hf, count[hf], threadIdx.x & 31u),
+                 make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), __float_as_uint(v.x)),
+                 make_uint4(__float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(r), z | ((unsigned)zone_index << 2)));
+        ++count[hf];
+    }
+};
+
+template <bool SPIN>
+__global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(const __grid_constant__ FrameArgs A, const __grid_constant__ SplitArgs S) {
+    using rrtp::F2;
+    using rrtp::V3x2;
+    __shared__ unsigned chunk_tab[kDescChunks];
+    const Consts& C = A.C;
+    const int lane = threadIdx.x & 31;
+    unsigned* tab = chunk_tab;
+    for (int j = lane; j < kDescChunks; j += 32) tab[j] = kNone;
+    __syncwarp();
+    const unsigned ntiles = num_tiles16(A);
+    const int max_steps = C.max_steps;
+    const bool want_disk = (C.flags & RRT_FLAG_DISK) != 0, want_dust = (C.flags & RRT_FLAG_DUST) != 0;
+    const float zone_rmax = fmaxf(18.0f, fmaxf(C.disk_zone_r, C.dust_zone_r));
+    const V3 cam_p = mk(A.cam.pos[0], A.cam.pos[1], A.cam.pos[2]);
+    const bool fast_ok = rrt::dot3(cam_p, cam_p) < 1.0e8f && C.acc_rmin < C.horizon_r && C.horizon_r >= 1e-3f;
+    const float redo_below = fast_ok ? C.acc_rmin : __int_as_float(0x7f800000);
+    const V3 park_p = mk(0.0f, 100.0f, 0.0f), park_v = mk(0.0f, 0.0f, 0.0f);   // inert state of a finished half, see render_kernel_p
+#if RRT_BURST_K > 0
+    constexpr int kBurst = RRT_BURST_K;
+    const float burst_min = fmaxf(zone_rmax, fmaxf(C.horizon_r, redo_below));
+    const float burst_margin = 1.25f * (float)kBurst * C.h[0];
+    const float burst_lo = burst_min + burst_margin, burst_hi = 250.0f - burst_margin;
+#endif
+    TileCounters cnt;
+    Emitter2 em(S, tab, C);
+    unsigned taken = 0, row_next = 0;
+
+    for (;;) {
+        const unsigned tile = next_tile(A, S, ntiles, true);
+        if (tile == kNone) break;
+        ++taken;
+        if (!stock_chunks(S, tab, row_next, 2u * ((unsigned)max_steps + 1u) + 1u, lane)) {
+            redo_later(S, tile, lane);
+            continue;
+        }
+        const TilePix px0 = tile_pixel16(A, tile, lane, 0), px1 = tile_pixel16(A, tile, lane, 1);
+        const int x0 = px0.x, y = px0.y, ly = px0.ly;
+        bool alive[2] = {px0.valid, px1.valid};
+        em.row0 = row_next;
+        em.count[0] = em.count[1] = 0u;
+        if (alive[0] || alive[1]) {
+            V3x2 P, V;
+            {
+                const V3 vA = alive[0] ? ray_dir(A, x0, y) : park_v, vB = alive[1] ? ray_dir(A, x0 + 1, y) : park_v;
+                const V3 pA = alive[0] ? cam_p : park_p, pB = alive[1] ? cam_p : park_p;
+                P.x = rrtp::pk(pA.x, pB.x); P.y = rrtp::pk(pA.y, pB.y); P.z = rrtp::pk(pA.z, pB.z);
+                V.x = rrtp::pk(vA.x, vB.x); V.y = rrtp::pk(vA.y, vB.y); V.z = rrtp::pk(vA.z, vB.z);
+            }
+            unsigned n_disk = 0, n_dust = 0;
+            // retire one half: a ray without samples is finished here, one with samples leaves its exit state behind them
+            auto retire = [&](int hf, int steps, unsigned end) {
+                const V3 p = rrtp::half_of(P, hf), v = rrtp::half_of(V, hf);
+                if (em.count[hf] == 0u) {
+                    finish_ray(A, x0 + hf, y, ly, 0.f, 0.f, 0.f, (end & kEndCaptured) ? 0.0f : 1.0f, p, v, steps, end);
+                } else {
+                    pool_put(S.slots, em.slot(hf, em.count[hf], (unsigned)lane),
+                             make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(v.x)),
+                             make_uint4(__float_as_uint(v.y), __float_as_uint(v.z), (unsigned)steps | (end << 28), 0u));
+                }
+                cnt.steps += (unsigned)steps;
+                cnt.cap += (end & kEndCaptured) ? 1u : 0u;
+                cnt.exh += (end & kEndExhausted) ? 1u : 0u;
+                cnt.esc += (end & (kEndCaptured | kEndExhausted)) ? 0u : 1u;
+                alive[hf] = false;
+                rrtp::set_half(P, hf, park_p);
+                rrtp::set_half(V, hf, park_v);
+            };
+
+            int it = 0;
+            int burst_after = 0;
+            F2 R2 = rrtp::norm2_loop_2(P);
+            F2 R = rrtp::sqrt2(R2);                                                              // :44
+            for (;;) {
+#if RRT_BURST_K > 0
+                // ---- phase 1: unchecked vacuum bursts, warp-uniform (see render_kernel_p / trace_ray) ------------------
+                {
+                    const unsigned in_loop = __activemask();
+                    const F2 H = rrtp::bc(C.h[0]), HH = rrtp::bc(C.hh[0]), H6 = rrtp::bc(C.h6[0]);
+#pragma unroll 1
+                    for (;;) {
+                        float r0, r1;
+                        rrtp::upk(R, r0, r1);
+                        const bool ok = fminf(r0, r1) >= burst_lo && fmaxf(r0, r1) <= burst_hi && it >= burst_after && it + kBurst < max_steps;
+                        if (!(ok && __activemask() == in_loop)) break;
+                        const V3x2 Ps = P, Vs = V;
+                        const F2 R2s = R2, Rs = R;
+                        float mn = fminf(r0, r1), mx = fmaxf(r0, r1);
+#pragma unroll 1
+                        for (int kb = 0; kb < kBurst; ++kb) {
+                            float ma, mb;
+                            rrtp::rk4_step2<SPIN>(C, P, V, H, HH, H6, R2, R, ma, mb);            // :64
+                            R2 = rrtp::norm2_loop_2(P);
+                            R = rrtp::sqrt2(R2);
+                            rrtp::upk(R, r0, r1);
+                            mn = fminf(mn, fminf(fminf(ma, mb), fminf(r0, r1)));
+                            mx = fmaxf(mx, fmaxf(r0, r1));
+                        }
+                        if (mn >= burst_min && mx <= 250.0f) { it += kBurst; continue; }
+                        P = Ps; V = Vs; R2 = R2s; R = Rs;
+                        burst_after = it + kBurst;
+                        break;
+                    }
+                }
+#endif
+                // ---- phase 2: checked iterations ----------------------------------------------------------------------
+                bool rewind = false;
+#pragma unroll 1
+                while (it < max_steps) {                                                         // :41
+                    float r[2];
+                    rrtp::upk(R, r[0], r[1]);
+                    bool parked = false;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        if (alive[hf] && r[hf] < C.horizon_r) {                                  // :47-51
+                            retire(hf, it, kEndCaptured);
+                            parked = true;
+                        }
+                    if (!(alive[0] || alive[1])) break;
+                    if (parked) {
+                        R2 = rrtp::norm2_loop_2(P);
+                        R = rrtp::sqrt2(R2);
+                        rrtp::upk(R, r[0], r[1]);
+                    }
+                    float h[2], h6[2];
+                    unsigned zones[2];
+                    int zidx[2];
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        h[hf] = C.h[0];
+                        h6[hf] = C.h6[0];
+                        zones[hf] = 0u;
+                        zidx[hf] = 0;
+                        if (r[hf] < zone_rmax) {
+                            const float py = rrtp::half_of(P.y, hf);
+                            const bool near_bh = r[hf] < 18.0f;                                  // :56
+                            const bool disk_zone = fabsf(py) < C.disk_zone_y && r[hf] < C.disk_zone_r;   // :57
+                            const bool dust_zone = fabsf(py) < C.dust_zone_y && r[hf] < C.dust_zone_r;   // :58
+                            const int zi = near_bh ? 1 : (disk_zone ? 2 : (dust_zone ? 3 : 0));  // :60-62
+                            h[hf] = C.h[zi];
+                            h6[hf] = C.h6[zi];
+                            zidx[hf] = zi;
+                            zones[hf] = (disk_zone && want_disk ? 1u : 0u) | (dust_zone && want_dust ? 2u : 0u);   // :67
+                        }
+                    }
+                    const F2 H = rrtp::pk(h[0], h[1]), H6 = rrtp::pk(h6[0], h6[1]);
+                    const F2 HH = rrtp::mul2(H, rrtp::bc(0.5f));   // exact (power of two)
+                    const V3x2 Q = P, Vin = V;         // pre-step state: media and the escape test use Q (:68-69, :120)
+                    float rmin[2];
+                    rrtp::rk4_step2<SPIN>(C, P, V, H, HH, H6, R2, R, rmin[0], rmin[1]);          // :64
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        if (alive[hf] && !(rmin[hf] >= redo_below)) {   // general-domain redo, see trace_ray
+                            const PV sres = rk4_step_general<SPIN>(C, rrtp::half_of(Q, hf), rrtp::half_of(Vin, hf), h[hf], h[hf] * 0.5f, h6[hf]);
+                            rrtp::set_half(P, hf, sres.p);
+                            rrtp::set_half(V, hf, sres.v);
+                        }
+                    ++it;
+                    const F2 R2n = rrtp::norm2_loop_2(P);
+                    const F2 Rn = rrtp::sqrt2(R2n);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        if (alive[hf] && zones[hf]) {                                            // :67
+                            n_disk += zones[hf] & 1u;
+                            n_dust += zones[hf] >> 1;
+                            em.emit(hf, rrtp::half_of(Q, hf), rrtp::half_of(V, hf), r[hf], zidx[hf], zones[hf]);
+                        }
+                    bool gone = false;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        if (alive[hf] && r[hf] > 250.0f && rrt::dot3(rrtp::half_of(Q, hf), rrtp::half_of(V, hf)) > 0.0f) {   // :120
+                            retire(hf, it, 0u);
+                            gone = true;
+                        }
+                    if (!(alive[0] || alive[1])) break;
+                    if (gone) {
+                        R2 = rrtp::norm2_loop_2(P);
+                        R = rrtp::sqrt2(R2);
+                    } else {
+                        R2 = R2n;
+                        R = Rn;
+                    }
+#if RRT_BURST_K > 0
+                    {
+                        const unsigned in_loop = __activemask();
+                        float r0, r1;
+                        rrtp::upk(R, r0, r1);
+                        if (fminf(r0, r1) >= burst_lo && fmaxf(r0, r1) <= burst_hi && it >= burst_after && it + kBurst < max_steps &&
+                            __activemask() == in_loop) { rewind = true; break; }
+                    }
+#endif
+                }
+                if (!rewind) break;
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                if (alive[hf]) retire(hf, it, kEndExhausted);  // the loop ran out (:41)
+            cnt.disk += n_disk; cnt.dust += n_dust;
+        }
+        __syncwarp();
+        // queue the halves that stored samples; the rows of the two halves interleave
+        const unsigned most = __reduce_max_sync(0xffffffffu, max(em.count[0], em.count[1]));
+        if (most != 0u) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+                if (__any_sync(0xffffffffu, em.count[hf] != 0u)) queue_group(S, tab, tile, em.row0 + (unsigned)hf, 2u, 1u + (unsigned)hf, em.count[hf], lane);
+            advance_rows(S, tab, row_next, 2u * (most + 1u), lane);
+        }
+    }
+    if (lane == 0 && taken) {
+        atomicMax(S.stats + 0, S.pass + 1u);
+        atomicAdd(S.stats + 2, taken);
+    }
+    cnt.flush(A.counters);
+}
+#endif  // RRT_FMAD
+
 // slot of (lane, k-th sample) of a queued tile, given the tile's chunk table
-__device__ __forceinline__ unsigned desc_slot(const SplitArgs& S, const unsigned* chunk, unsigned row0, unsigned k, unsigned lane) {
-    const unsigned pos = row0 + k;
+__device__ __forceinline__ unsigned desc_slot(const SplitArgs& S, const unsigned* chunk, unsigned row0, unsigned stride, unsigned k, unsigned lane) {
+    const unsigned pos = row0 + k * stride;
     return chunk[pos >> S.chunk_shift] + (pos & (S.chunk_rows - 1u)) * 32u + lane;
 }
 
@@ -414,7 +704,7 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
             const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += up;
         }
-        const unsigned row0 = d->row0, total = d->total;
+        const unsigned row0 = d->row0, total = d->total, stride = d->stride_kind & 0xffu;
         pref[lane + 1] = incl;
         if (lane == 0) pref[0] = 0u;
         for (int j = lane; j < kDescChunks; j += 32) chunk[j] = d->chunk[j];
@@ -433,7 +723,7 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
                     const unsigned mid = (lo + hi) >> 1;
                     if (pref[mid] <= sidx) lo = mid; else hi = mid;
                 }
-                slot = desc_slot(S, chunk, row0, sidx - pref[lo], lo);
+                slot = desc_slot(S, chunk, row0, stride, sidx - pref[lo], lo);
                 tag = S.slots[2ull * slot + 1].w;
                 a = S.slots[2ull * slot];
             }
@@ -498,10 +788,15 @@ __global__ void __launch_bounds__(128) fold_kernel(const __grid_constant__ Frame
         __syncwarp();
         for (int j = lane; j < kDescChunks; j += 32) chunk[j] = d->chunk[j];
         __syncwarp();
-        const unsigned row0 = d->row0, n = d->n[lane];
-        const TilePix px = tile_pixel(A, d->tile, lane);
-        const unsigned st = desc_slot(S, chunk, row0, d->n_rows, (unsigned)lane);
-        const uint4 sa = S.slots[2ull * st], sb = S.slots[2ull * st + 1];
+        const unsigned row0 = d->row0, n = d->n[lane], stride = d->stride_kind & 0xffu, kind = d->stride_kind >> 8;
+        const TilePix px = kind == 0u ? tile_pixel(A, d->tile, lane) : tile_pixel16(A, d->tile, lane, (int)kind - 1);
+        // a lane without samples finished its ray in the trace kernel; the others left their exit state behind their samples
+        uint4 sa = make_uint4(0u, 0u, 0u, 0u), sb = sa;
+        if (n) {
+            const unsigned st = desc_slot(S, chunk, row0, stride, n, (unsigned)lane);
+            sa = S.slots[2ull * st];
+            sb = S.slots[2ull * st + 1];
+        }
         const V3 p = mk(__uint_as_float(sa.x), __uint_as_float(sa.y), __uint_as_float(sa.z));
         const V3 v = mk(__uint_as_float(sa.w), __uint_as_float(sb.x), __uint_as_float(sb.y));
         const int steps = (int)(sb.z & 0x0fffffffu);
@@ -513,7 +808,7 @@ __global__ void __launch_bounds__(128) fold_kernel(const __grid_constant__ Frame
             uint4 e[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                e[u] = k0 + u < n ? S.slots[2ull * desc_slot(S, chunk, row0, k0 + u, (unsigned)lane)] : make_uint4(0u, 0u, 0u, 0xbf800000u);
+                e[u] = k0 + u < n ? S.slots[2ull * desc_slot(S, chunk, row0, stride, k0 + u, (unsigned)lane)] : make_uint4(0u, 0u, 0u, 0xbf800000u);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const float s = __uint_as_float(e[u].w);
@@ -529,7 +824,7 @@ __global__ void __launch_bounds__(128) fold_kernel(const __grid_constant__ Frame
         }
         if (n_dense) end |= kEndTouched;
         if (end & kEndCaptured) T = 0.0f;                                                     // :49
-        if (px.valid) {
+        if (px.valid && n) {
             float uvx, uvy;
             pixel_uv(A, px.x, px.y, uvx, uvy);
             finish_ray_inl(A, px.x, px.y, px.ly, uvx, uvy, Ir, Ig, Ib, T, p, v, steps, end);
@@ -548,28 +843,43 @@ __global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS_MEDIA) sweep_kern
     const unsigned ntiles = num_tiles(A);
     TileCounters cnt;
     unsigned taken = 0;
+    const int ntx16 = (A.w + kTile16W - 1) / kTile16W, ntx8 = (A.w + kRTileW - 1) / kRTileW;
     for (;;) {
-        const unsigned tile = next_tile(A, S, ntiles, false);
-        if (tile == kNone) break;
+        const unsigned ticket = next_tile(A, S, S.tile16 ? num_tiles16(A) : ntiles, false);
+        if (ticket == kNone) break;
         ++taken;
-        const TilePix px = tile_pixel(A, tile, lane);
-        if (!px.valid) continue;
-        RayResult R;
-        NoEmit no_emit;
-        trace_ray<SPIN, kMediaInline>(A, px.x, px.y, R, no_emit);
-        finish_ray_inl(A, px.x, px.y, px.ly, R.uvx, R.uvy, R.I[0], R.I[1], R.I[2], R.T, R.p, R.v, R.steps,
-                       (R.captured ? kEndCaptured : 0u) | (R.touched ? kEndTouched : 0u) | (R.exhausted ? kEndExhausted : 0u));
-        cnt.steps += (unsigned)R.steps;
-        cnt.disk += R.n_disk; cnt.dust += R.n_dust; cnt.dense += R.n_dense;
-        cnt.cap += R.captured; cnt.exh += R.exhausted; cnt.esc += (!R.captured && !R.exhausted); cnt.touch += R.touched;
+        for (int sub = 0; sub < (S.tile16 ? 2 : 1); ++sub) {
+            unsigned tile = ticket;
+            if (S.tile16) {   // a 16x4 tile of the packed tracer = the 8x4 tiles (2 tx, ty) and (2 tx + 1, ty), same row order
+                const int tx8 = 2 * (int)(ticket % (unsigned)ntx16) + sub;
+                if (tx8 >= ntx8) continue;
+                tile = (ticket / (unsigned)ntx16) * (unsigned)ntx8 + (unsigned)tx8;
+            }
+            const TilePix px = tile_pixel(A, tile, lane);
+            if (!px.valid) continue;
+            RayResult R;
+            NoEmit no_emit;
+            trace_ray<SPIN, kMediaInline>(A, px.x, px.y, R, no_emit);
+            finish_ray_inl(A, px.x, px.y, px.ly, R.uvx, R.uvy, R.I[0], R.I[1], R.I[2], R.T, R.p, R.v, R.steps,
+                           (R.captured ? kEndCaptured : 0u) | (R.touched ? kEndTouched : 0u) | (R.exhausted ? kEndExhausted : 0u));
+            cnt.steps += (unsigned)R.steps;
+            cnt.disk += R.n_disk; cnt.dust += R.n_dust; cnt.dense += R.n_dense;
+            cnt.cap += R.captured; cnt.exh += R.exhausted; cnt.esc += (!R.captured && !R.exhausted); cnt.touch += R.touched;
+        }
     }
     if (lane == 0 && taken) atomicAdd(S.stats + 1, taken);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { S.stats[3] = S.pass; S.stats[4] = ntiles; }   // what the host enqueued, for its next guess
+    if (blockIdx.x == 0 && threadIdx.x == 0) { S.stats[3] = S.pass; S.stats[4] = S.tile16 ? num_tiles16(A) : ntiles; }   // what the host enqueued, for its next guess
     cnt.flush(A.counters);
 }
 
 const rrtk::SplitKernels kSplitKernels = {
-    {trace_kernel<false>, trace_kernel<true>}, media_kernel, fold_kernel, {sweep_kernel<false>, sweep_kernel<true>},
+    {trace_kernel<false>, trace_kernel<true>},
+#if RRT_FMAD
+    {trace_kernel_p<false>, trace_kernel_p<true>},
+#else
+    {nullptr, nullptr},
+#endif
+    media_kernel, fold_kernel, {sweep_kernel<false>, sweep_kernel<true>},
 };
 }  // namespace
 
