@@ -548,7 +548,7 @@ static int render_split(rrt_context* ctx, const FrameArgs& A, bool spin, bool fm
     unsigned* redo = (unsigned*)(pl->d_ctrl + kCtrlHead);
 
     RRT_CU(ctx, cudaMemsetAsync(pl->d_ctrl, 0, kCtrlHead, st));
-    const int per_sm_media = resident_per_sm(ctx, (const void*)sk->media, kMediaBlock, false);
+    const int per_sm_media = resident_per_sm(ctx, (const void*)sk->media, kMediaBlock, true);
     const int per_sm_fold = resident_per_sm(ctx, (const void*)sk->fold, 128, false);
     const int per_sm_sweep = resident_per_sm(ctx, (const void*)k_sweep, kRenderBlock, true);
     for (int p = 0; p < passes; ++p) {

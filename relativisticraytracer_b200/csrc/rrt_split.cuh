@@ -674,10 +674,17 @@ __device__ __forceinline__ unsigned desc_slot(const SplitArgs& S, const unsigned
 // Stage 1 evaluates, lane per sample, the disk density and the dust envelope.  The dust strands -- 19 value-noise
 // evaluations, needed only where the envelope survived its 0.001 cut (densities.h:84) -- are collected over the whole
 // batch and evaluated 32 at a time.  Stage 3 is media_final for every sample.
+__device__ __forceinline__ void pool_get(const uint4* slots, unsigned slot, uint4& a, uint4& b) {   // one 256-bit load
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(slots + 2ull * slot));
+}
 __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_constant__ FrameArgs A, const __grid_constant__ SplitArgs S) {
     __shared__ float s_dd[kMediaBlock / 32][kMediaBatch];
     __shared__ float s_dc[kMediaBlock / 32][kMediaBatch];      // dust envelope, then dust density
     __shared__ unsigned s_slot[kMediaBlock / 32][kMediaBatch];
+    __shared__ uint4 s_a[kMediaBlock / 32][kMediaBatch];       // the batch's samples: {q.xyz, v.x}
+    __shared__ uint4 s_b[kMediaBlock / 32][kMediaBatch];       //                      {v.y, v.z, r, tag}
     __shared__ unsigned short s_list[kMediaBlock / 32][kMediaBatch];
     __shared__ unsigned s_chunk[kMediaBlock / 32][kDescChunks];
     __shared__ unsigned s_pref[kMediaBlock / 32][33];
@@ -687,6 +694,8 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
     float* dd_w = s_dd[warp];
     float* dc_w = s_dc[warp];
     unsigned* slot_w = s_slot[warp];
+    uint4* a_w = s_a[warp];
+    uint4* b_w = s_b[warp];
     unsigned short* list = s_list[warp];
     unsigned* chunk = s_chunk[warp];
     unsigned* pref = s_pref[warp];
@@ -699,35 +708,52 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
         const TileDesc* d = S.desc + w.desc;
         // samples per lane -> exclusive prefix: sample index -> (lane, k)
         unsigned incl = d->n[lane];
+        const unsigned row0 = d->row0, total = d->total, stride = d->stride_kind & 0xffu;
+        for (int j = lane; j < kDescChunks; j += 32) chunk[j] = d->chunk[j];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += up;
         }
-        const unsigned row0 = d->row0, total = d->total, stride = d->stride_kind & 0xffu;
         pref[lane + 1] = incl;
         if (lane == 0) pref[0] = 0u;
-        for (int j = lane; j < kDescChunks; j += 32) chunk[j] = d->chunk[j];
+        __syncwarp();
+        // fetch: the whole batch's samples into shared memory, all loads of a lane in flight together
+        {
+            unsigned slot[kMediaBatch / 32];
+            uint4 a[kMediaBatch / 32], b[kMediaBatch / 32];
+#pragma unroll
+            for (int k = 0; k < kMediaBatch / 32; ++k) {
+                const unsigned sidx = w.first + (unsigned)k * 32u + (unsigned)lane;
+                slot[k] = kNone;
+                a[k] = b[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (sidx < total) {
+                    unsigned lo = 0u, hi = 32u;   // largest l with pref[l] <= sidx
+#pragma unroll
+                    for (int bb = 0; bb < 5; ++bb) {
+                        const unsigned mid = (lo + hi) >> 1;
+                        if (pref[mid] <= sidx) lo = mid; else hi = mid;
+                    }
+                    slot[k] = desc_slot(S, chunk, row0, stride, sidx - pref[lo], lo);
+                    pool_get(S.slots, slot[k], a[k], b[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kMediaBatch / 32; ++k) {
+                const unsigned i = (unsigned)k * 32u + (unsigned)lane;
+                slot_w[i] = slot[k];
+                a_w[i] = a[k];
+                b_w[i] = b[k];
+            }
+        }
         __syncwarp();
         unsigned n_list = 0;
         // stage 1
 #pragma unroll 1
         for (int k = 0; k < kMediaBatch / 32; ++k) {
-            const unsigned i = (unsigned)k * 32u + (unsigned)lane, sidx = w.first + i;
-            unsigned tag = 0u, slot = kNone;
-            uint4 a = make_uint4(0u, 0u, 0u, 0u);
-            if (sidx < total) {
-                unsigned lo = 0u, hi = 32u;   // largest l with pref[l] <= sidx
-#pragma unroll
-                for (int b = 0; b < 5; ++b) {
-                    const unsigned mid = (lo + hi) >> 1;
-                    if (pref[mid] <= sidx) lo = mid; else hi = mid;
-                }
-                slot = desc_slot(S, chunk, row0, stride, sidx - pref[lo], lo);
-                tag = S.slots[2ull * slot + 1].w;
-                a = S.slots[2ull * slot];
-            }
-            slot_w[i] = slot;
+            const unsigned i = (unsigned)k * 32u + (unsigned)lane;
+            const uint4 a = a_w[i];
+            const unsigned tag = b_w[i].w;   // 0 for the lanes behind the group's last sample
             float dd = 0.0f, base_d = 0.0f;
             const V3 q = mk(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
             if (tag & 1u) dd = rrt::disk_density(C, q, A.time);                               // :68
@@ -749,7 +775,7 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
             const unsigned j = j0 + (unsigned)lane;
             if (j < n_list) {
                 const unsigned i = list[j];
-                const uint4 a = S.slots[2ull * slot_w[i]];
+                const uint4 a = a_w[i];
                 const V3 q = mk(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
                 dc_w[i] = rrt::dust_strands(C, q, A.time, dc_w[i]);
             }
@@ -760,7 +786,7 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
         for (int k = 0; k < kMediaBatch / 32; ++k) {
             const unsigned i = (unsigned)k * 32u + (unsigned)lane, slot = slot_w[i];
             if (slot != kNone) {
-                const uint4 a = S.slots[2ull * slot], b = S.slots[2ull * slot + 1];
+                const uint4 a = a_w[i], b = b_w[i];
                 const V3 q = mk(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
                 const V3 v = mk(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
                 const MediaOut m = media_final(C, q, v, __uint_as_float(b.z), C.h[(b.w >> 2) & 3u], dd_w[i], dc_w[i]);
