@@ -151,23 +151,24 @@ class BandedFrame:
 
     def render(self, prm, cam, fx, sky, time: float) -> int:
         """Trace this rank's rows and bring them together on rank 0.  Returns how many of OUR kernels were launched."""
+        l0 = self.r.kernel_launches()   # the context counts its own kernels (1 fused, or 3 per pass + 1 in the split pipeline)
         if self.world == 1:
             self.r.render(prm, cam, fx, sky, time, self.w, self.h, out=self.frame)
-            return 1
+            return self.r.kernel_launches() - l0
         if self.exchange == "peer":
             # the store that ends the path is the exchange; the all-reduce orders rank 0's consumers after every band
             self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.peer)
             dist.all_reduce(self.token)
             if self.rank == 0:
                 self.peer.read_into(self.frame)     # 33 MB device-to-device at 4K (~10 us): hands the frame to torch
-            return 1
+            return self.r.kernel_launches() - l0
         self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.packed, layout=OUT_PACKED)
         if self.rank == 0:
             dist.gather(self.packed, list(self.gathered.unbind(0)), dst=0)
             self.r.assemble_bands(self.gathered, self.rows_max, self.w, self.h, self.world, self.group, frame=self.frame)
-            return 2
+            return self.r.kernel_launches() - l0
         dist.gather(self.packed, None, dst=0)
-        return 1
+        return self.r.kernel_launches() - l0
 
 
 class FramePipeline:
@@ -229,6 +230,7 @@ class FramePipeline:
         k = self.submitted % self.depth
         self.submitted += 1
         s = self.streams[k]
+        l0 = self.r.kernel_launches()   # the context counts its own kernels (1 fused, or 3 per pass + 1 in the split pipeline)
         if self.world == 1:
             if self.to_host:   # the C-ABI call with a HOST destination, asynchronous flavour
                 self.r.render_host_async(prm, cam, fx, sky, time, self.w, self.h, self.host_frames[k], slot=k, stream=s)
@@ -236,8 +238,7 @@ class FramePipeline:
                 self.r.render(prm, cam, fx, sky, time, self.w, self.h, out=self.frames[k], stream=s)
             self.done[k].record(s)
             self.busy[k] = True
-            return 1
-        launches = 1
+            return self.r.kernel_launches() - l0
         if self.exchange == "peer":
             with torch.cuda.stream(s):
                 # every rank's kernel stores its rows straight into slot k of rank 0's frames; all-reduce #1 tells rank 0
@@ -250,21 +251,20 @@ class FramePipeline:
                 dist.all_reduce(self.tokens[k])
                 self.done[k].record(s)
             self.busy[k] = True
-            return launches
+            return self.r.kernel_launches() - l0
         with torch.cuda.stream(s):
             self.r.render(prm, cam, fx, sky, time, self.w, self.h, band=self.band, out=self.packed[k], layout=OUT_PACKED, stream=s)
             if self.rank == 0:
                 dist.gather(self.packed[k], list(self.gathered[k].unbind(0)), dst=0)
                 self.r.assemble_bands(self.gathered[k], self.rows_max, self.w, self.h, self.world, self.group,
                                       frame=self.frames[k], stream=s)
-                launches += 1
                 if self.to_host:
                     self.host_frames[k].copy_(self.frames[k], non_blocking=True)
             else:
                 dist.gather(self.packed[k], None, dst=0)
             self.done[k].record(s)
         self.busy[k] = True
-        return launches
+        return self.r.kernel_launches() - l0
 
     def wait_slot(self, k: int) -> None:
         """Block the host until the frame last submitted to slot k is complete (its destination may then be read, and
@@ -327,7 +327,8 @@ class PathSequence:
         schedule = path_rounds(n_frames, self.world, first_frame)
         rounds = len(schedule)
         in_flight = [None] * self.depth     # per slot: list of frame numbers it holds
-        launches = done = 0
+        done = 0
+        l0 = self.r.kernel_launches()       # the context counts its own kernels
 
         def retire(k):
             nonlocal done
@@ -352,13 +353,11 @@ class PathSequence:
                     t = path_clock(mine, fps)
                     cam, _ = path_state(path_index, t)
                     self.r.render_host_async(prm, cam, fx, sky, t, self.w, self.h, self.host[k][0], slot=k, stream=s)
-                    launches += 1
                 else:
                     if mine is not None:
                         t = path_clock(mine, fps)
                         cam, _ = path_state(path_index, t)
                         self.r.render(prm, cam, fx, sky, t, self.w, self.h, out=self.local[k], stream=s)
-                        launches += 1
                     if self.rank == 0:
                         dist.gather(self.local[k], list(self.gathered[k].unbind(0)), dst=0)
                         self.host[k].copy_(self.gathered[k], non_blocking=True)
@@ -370,4 +369,4 @@ class PathSequence:
             retire(j % self.depth)
         for s in self.streams:
             cur.wait_stream(s)
-        return done, launches
+        return done, self.r.kernel_launches() - l0
