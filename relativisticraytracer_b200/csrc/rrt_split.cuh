@@ -468,6 +468,17 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
     const float burst_min = fmaxf(zone_rmax, fmaxf(C.horizon_r, redo_below));
     const float burst_margin = 1.25f * (float)kBurst * C.h[0];
     const float burst_lo = burst_min + burst_margin, burst_hi = 250.0f - burst_margin;
+    // Zone bursts (RRT_ZONE_BURSTS): the same idea inside the two step-size zones that matter -- near the hole (r < 18, step
+    // h[1]) and in the disk zone (r >= 18, |y| < DISK_H * 5, r < DISK_OUT + 5, step h[2]); reference raymarcher.cu:56-62.  While
+    // every ray of the warp sits well inside ONE of them, kBurst steps are taken with that zone's step as a uniform operand
+    // and none of the per-half zone logic; each step still stores its media sample (the zone flags of a sample do not
+    // influence the trajectory).  Afterwards the burst is validated -- every pre-step state must have been in that zone,
+    // above the horizon and in the branch-free domain -- and rolled back otherwise (the samples it stored are overwritten).
+    const float zb_floor = fmaxf(C.horizon_r, redo_below);
+    const float zb_m1 = 1.25f * (float)kBurst * C.h[1], zb_m2 = 1.25f * (float)kBurst * C.h[2];
+    const float near_lo = zb_floor + zb_m1, near_hi = 18.0f - zb_m1;
+    const float disk_lo = 18.0f + zb_m2, disk_hi = C.disk_zone_r - zb_m2, disk_y = C.disk_zone_y - zb_m2;
+    const float kInf = __int_as_float(0x7f800000);
 #endif
     TileCounters cnt;
     Emitter2 em(S, tab, C);
@@ -515,7 +526,7 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
             };
 
             int it = 0;
-            int burst_after = 0;
+            int burst_after = 0, zburst_after = 0;
             F2 R2 = rrtp::norm2_loop_2(P);
             F2 R = rrtp::sqrt2(R2);                                                              // :44
             for (;;) {
@@ -548,6 +559,63 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
                         burst_after = it + kBurst;
                         break;
                     }
+#ifndef RRT_NO_ZONE_BURSTS
+                    // ---- phase 1b: zone bursts ---------------------------------------------------------------------------
+#pragma unroll 1
+                    for (;;) {
+                        float r0, r1, y0, y1;
+                        rrtp::upk(R, r0, r1);
+                        rrtp::upk(P.y, y0, y1);
+                        y0 = fabsf(y0); y1 = fabsf(y1);
+                        const bool can = it >= zburst_after && it + kBurst < max_steps;
+                        // a parked half qualifies for everything
+                        const bool near_ok = can && (!alive[0] || (r0 >= near_lo && r0 <= near_hi)) && (!alive[1] || (r1 >= near_lo && r1 <= near_hi));
+                        const bool disk_ok = can && (!alive[0] || (r0 >= disk_lo && r0 <= disk_hi && y0 < disk_y)) &&
+                                             (!alive[1] || (r1 >= disk_lo && r1 <= disk_hi && y1 < disk_y));
+                        int mode = 0;
+                        if (near_ok && __activemask() == in_loop) mode = 1;
+                        else if (disk_ok && __activemask() == in_loop) mode = 2;
+                        if (mode == 0) break;
+                        const F2 ZH = rrtp::bc(C.h[mode]), ZHH = rrtp::bc(C.hh[mode]), ZH6 = rrtp::bc(C.h6[mode]);
+                        const V3x2 Ps = P, Vs = V;
+                        const F2 R2s = R2, Rs = R;
+                        const unsigned c0s = em.count[0], c1s = em.count[1];
+                        unsigned bd = 0, bu = 0;
+                        float mn = kInf, mx = 0.0f, my = 0.0f;
+#pragma unroll 1
+                        for (int kb = 0; kb < kBurst; ++kb) {
+                            const V3x2 Q = P;
+                            float q0, q1, yy0, yy1, ma, mb;
+                            rrtp::upk(R, q0, q1);             // pre-step radii
+                            rrtp::upk(P.y, yy0, yy1);
+                            yy0 = fabsf(yy0); yy1 = fabsf(yy1);
+                            rrtp::rk4_step2<SPIN>(C, P, V, ZH, ZHH, ZH6, R2, R, ma, mb);         // :64
+                            R2 = rrtp::norm2_loop_2(P);
+                            R = rrtp::sqrt2(R2);
+                            if (alive[0]) {
+                                mn = fminf(mn, fminf(q0, ma)); mx = fmaxf(mx, q0); my = fmaxf(my, yy0);
+                                const unsigned z = (yy0 < C.disk_zone_y && q0 < C.disk_zone_r && want_disk ? 1u : 0u) |
+                                                   (yy0 < C.dust_zone_y && q0 < C.dust_zone_r && want_dust ? 2u : 0u);      // :57-58, :67
+                                if (z) { bd += z & 1u; bu += z >> 1; em.emit(0, rrtp::half_of(Q, 0), rrtp::half_of(V, 0), q0, mode, z); }
+                            }
+                            if (alive[1]) {
+                                mn = fminf(mn, fminf(q1, mb)); mx = fmaxf(mx, q1); my = fmaxf(my, yy1);
+                                const unsigned z = (yy1 < C.disk_zone_y && q1 < C.disk_zone_r && want_disk ? 1u : 0u) |
+                                                   (yy1 < C.dust_zone_y && q1 < C.dust_zone_r && want_dust ? 2u : 0u);
+                                if (z) { bd += z & 1u; bu += z >> 1; em.emit(1, rrtp::half_of(Q, 1), rrtp::half_of(V, 1), q1, mode, z); }
+                            }
+                        }
+                        // every pre-step state in the zone the step size came from (:56-62), above the horizon (:47) and in the
+                        // branch-free domain; `mn` also holds the stage radii
+                        const bool good = mode == 1 ? (mn >= zb_floor && mx < 18.0f)
+                                                    : (mn >= 18.0f && mx < C.disk_zone_r && my < C.disk_zone_y);
+                        if (good) { it += kBurst; n_disk += bd; n_dust += bu; continue; }
+                        P = Ps; V = Vs; R2 = R2s; R = Rs;
+                        em.count[0] = c0s; em.count[1] = c1s;
+                        zburst_after = it + kBurst;
+                        break;
+                    }
+#endif
                 }
 #endif
                 // ---- phase 2: checked iterations ----------------------------------------------------------------------
@@ -634,6 +702,16 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
                         rrtp::upk(R, r0, r1);
                         if (fminf(r0, r1) >= burst_lo && fmaxf(r0, r1) <= burst_hi && it >= burst_after && it + kBurst < max_steps &&
                             __activemask() == in_loop) { rewind = true; break; }
+#ifndef RRT_NO_ZONE_BURSTS
+                        float y0, y1;
+                        rrtp::upk(P.y, y0, y1);
+                        y0 = fabsf(y0); y1 = fabsf(y1);
+                        const bool can = it >= zburst_after && it + kBurst < max_steps;
+                        if (can && (!alive[0] || (r0 >= near_lo && r0 <= near_hi)) && (!alive[1] || (r1 >= near_lo && r1 <= near_hi)) &&
+                            __activemask() == in_loop) { rewind = true; break; }
+                        if (can && (!alive[0] || (r0 >= disk_lo && r0 <= disk_hi && y0 < disk_y)) &&
+                            (!alive[1] || (r1 >= disk_lo && r1 <= disk_hi && y1 < disk_y)) && __activemask() == in_loop) { rewind = true; break; }
+#endif
                     }
 #endif
                 }
@@ -756,7 +834,11 @@ __global__ void __launch_bounds__(kMediaBlock, 4) media_kernel(const __grid_cons
             const unsigned tag = b_w[i].w;   // 0 for the lanes behind the group's last sample
             float dd = 0.0f, base_d = 0.0f;
             const V3 q = mk(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+#ifdef RRT_MEDIA_UNGATED
             if (tag & 1u) dd = rrt::disk_density(C, q, A.time);                               // :68
+#else
+            if (tag & 1u) dd = rrt::disk_density_gated(C, q, A.time);                         // :68 (0 where the gate of :71 cannot pass)
+#endif
             if (tag & 2u) base_d = rrt::dust_base(C, q);                                      // :69, densities.h:70-84
             dd_w[i] = dd;
             dc_w[i] = 0.0f;

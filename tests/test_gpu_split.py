@@ -6,6 +6,8 @@ bits as evaluating every sample on the spot: uchar4 frames, every parity plane (
 every counter, in both rounding contracts, for every camera / medium combination, ragged sizes, bands, the step budget's
 edges -- and for ANY pool size: a pool too small for the frame cuts it into passes, tiles that cannot get a slot are
 traced again by the next pass, and whatever the enqueued passes leave is rendered by the closing fused sweep."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,16 +16,32 @@ from parity import CAMERAS
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def pair(built):
+def _renderer_with_tracer(tracer):
+    """RRT_TRACE (scalar | packed | auto) is read when a context is created."""
+    import relativisticraytracer_b200 as rrt
+    old = os.environ.get("RRT_TRACE")
+    os.environ["RRT_TRACE"] = tracer
+    try:
+        return rrt.Renderer(0)
+    finally:
+        if old is None:
+            os.environ.pop("RRT_TRACE", None)
+        else:
+            os.environ["RRT_TRACE"] = old
+
+
+@pytest.fixture(scope="module", params=["packed", "scalar"])
+def pair(built, request):
+    """(fused, split) contexts; the split one with the packed f32x2 tracer (two rays per thread, the default under the FMAD
+    contract; the strict contract has only the scalar tracer) or the scalar one."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     import relativisticraytracer_b200 as rrt
-    fused, split = rrt.Renderer(0), rrt.Renderer(0)
+    fused, split = rrt.Renderer(0), _renderer_with_tracer(request.param)
     fused.set_pipeline("fused")
     split.set_pipeline("split")
-    yield fused, split
+    yield fused, split, request.param
     fused.close()
     split.close()
 
@@ -55,7 +73,7 @@ def _same(a, b, tag):
 @pytest.mark.parametrize("cam", ["C0", "C1", "C2", "C3"])
 @pytest.mark.parametrize("spin,flags", [(0.99, 7), (0.0, 7), (0.99, 5), (0.99, 6), (0.99, 3), (0.0, 1)])
 def test_split_equals_fused(pair, sky_small, cam, spin, flags):
-    fused, split = pair
+    fused, split, _ = pair
     w, h = 203, 117
     a, b = _frame(fused, sky_small, cam, spin, flags, w, h), _frame(split, sky_small, cam, spin, flags, w, h)
     _same(a, b, f"{cam} a={spin} flags={flags}")
@@ -67,7 +85,7 @@ def test_split_equals_fused(pair, sky_small, cam, spin, flags):
 
 def test_split_equals_fused_bands_budget_time_and_tiny_frames(pair, sky_small):
     import relativisticraytracer_b200 as rrt
-    fused, split = pair
+    fused, split, _ = pair
     for band in (rrt.Band(0, 3, 8), rrt.Band(2, 3, 8), rrt.Band(1, 2, 1)):
         _same(_frame(fused, sky_small, "C1", 0.99, 7, 160, 90, band=band), _frame(split, sky_small, "C1", 0.99, 7, 160, 90, band=band), f"band {band.rank}/{band.nranks}")
     for steps in (0, 1, 8, 9, 333, 1999):
@@ -86,8 +104,8 @@ def test_any_pool_size_gives_the_same_frame(built, sky_small, pair, pool_kib, ma
     """Pools from 'several passes' down to 'smaller than one disk-plane tile's samples' (then every such tile gives up in
     every pass and the closing fused sweep renders it): passes, redo lists and the sweep must all lead to the same frame."""
     import relativisticraytracer_b200 as rrt
-    fused, _ = pair
-    r = rrt.Renderer(0)
+    fused, _, tracer = pair
+    r = _renderer_with_tracer(tracer)
     try:
         r.set_pipeline("split")
         r.set_sample_pool(pool_kib * 1024, max_passes)
@@ -109,7 +127,7 @@ def test_frames_in_flight_on_several_streams(pair, sky_small):
     """Frames on different streams own different pools; five streams share four pools (stream-ordered reuse)."""
     import torch
     import relativisticraytracer_b200 as rrt
-    fused, split = pair
+    fused, split, _ = pair
     w, h = 160, 90
     sky_f, sky_s = fused.create_sky(sky_small), split.create_sky(sky_small)
     fx = rrt.default_effects()
@@ -135,5 +153,5 @@ def test_frames_in_flight_on_several_streams(pair, sky_small):
 
 @pytest.mark.parametrize("w,h,cam", [(1920, 1080, "C0"), (1920, 1080, "C3")])
 def test_split_equals_fused_1080p(pair, sky_small, w, h, cam):
-    fused, split = pair
+    fused, split, _ = pair
     _same(_frame(fused, sky_small, cam, 0.99, 7, w, h), _frame(split, sky_small, cam, 0.99, 7, w, h), f"{w}x{h} {cam}")
