@@ -468,17 +468,29 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
     const float burst_min = fmaxf(zone_rmax, fmaxf(C.horizon_r, redo_below));
     const float burst_margin = 1.25f * (float)kBurst * C.h[0];
     const float burst_lo = burst_min + burst_margin, burst_hi = 250.0f - burst_margin;
-    // Zone bursts (RRT_ZONE_BURSTS): the same idea inside the two step-size zones that matter -- near the hole (r < 18, step
-    // h[1]) and in the disk zone (r >= 18, |y| < DISK_H * 5, r < DISK_OUT + 5, step h[2]); reference raymarcher.cu:56-62.  While
-    // every ray of the warp sits well inside ONE of them, kBurst steps are taken with that zone's step as a uniform operand
-    // and none of the per-half zone logic; each step still stores its media sample (the zone flags of a sample do not
-    // influence the trajectory).  Afterwards the burst is validated -- every pre-step state must have been in that zone,
-    // above the horizon and in the branch-free domain -- and rolled back otherwise (the samples it stored are overwritten).
+    // Zone bursts: the same idea inside the two step-size zones that matter -- near the hole (r < 18, step h[1]) and in the
+    // disk zone (r >= 18, |y| < DISK_H * 5, r < DISK_OUT + 5, step h[2]); reference raymarcher.cu:56-62.  While every ray of
+    // the warp sits well inside SOME zone (each its own: vacuum counts), kBurst steps are taken with each ray's zone step
+    // and none of the per-step zone logic; each step still stores its media sample (the zone flags of a sample do not
+    // influence the trajectory).  Afterwards the burst is validated -- every pre-step state of a ray must have been in the
+    // zone its step came from, above the horizon, short of the escape sphere and in the branch-free domain -- and rolled
+    // back otherwise (the samples it stored are overwritten).
     const float zb_floor = fmaxf(C.horizon_r, redo_below);
     const float zb_m1 = 1.25f * (float)kBurst * C.h[1], zb_m2 = 1.25f * (float)kBurst * C.h[2];
     const float near_lo = zb_floor + zb_m1, near_hi = 18.0f - zb_m1;
     const float disk_lo = 18.0f + zb_m2, disk_hi = C.disk_zone_r - zb_m2, disk_y = C.disk_zone_y - zb_m2;
     const float kInf = __int_as_float(0x7f800000);
+    auto zone_for_burst = [&](float r, float ay) -> int {
+        if (r >= burst_lo && r <= burst_hi) return 0;
+        if (r >= near_lo && r <= near_hi) return 1;
+        if (r >= disk_lo && r <= disk_hi && ay < disk_y) return 2;
+        return -1;
+    };
+    auto burst_was_valid = [&](int m, float mn, float mx, float my) -> bool {
+        if (m == 0) return mn >= burst_min && mx <= 250.0f;                      // no zone, no medium, no escape test to miss
+        if (m == 1) return mn >= zb_floor && mx < 18.0f;                         // :56
+        return mn >= 18.0f && mx < C.disk_zone_r && my < C.disk_zone_y;          // :57 and not :56
+    };
 #endif
     TileCounters cnt;
     Emitter2 em(S, tab, C);
@@ -560,28 +572,22 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
                         break;
                     }
 #ifndef RRT_NO_ZONE_BURSTS
-                    // ---- phase 1b: zone bursts ---------------------------------------------------------------------------
+                    // ---- phase 1b: zone bursts, one zone per ray --------------------------------------------------------------
 #pragma unroll 1
                     for (;;) {
                         float r0, r1, y0, y1;
                         rrtp::upk(R, r0, r1);
                         rrtp::upk(P.y, y0, y1);
-                        y0 = fabsf(y0); y1 = fabsf(y1);
-                        const bool can = it >= zburst_after && it + kBurst < max_steps;
-                        // a parked half qualifies for everything
-                        const bool near_ok = can && (!alive[0] || (r0 >= near_lo && r0 <= near_hi)) && (!alive[1] || (r1 >= near_lo && r1 <= near_hi));
-                        const bool disk_ok = can && (!alive[0] || (r0 >= disk_lo && r0 <= disk_hi && y0 < disk_y)) &&
-                                             (!alive[1] || (r1 >= disk_lo && r1 <= disk_hi && y1 < disk_y));
-                        int mode = 0;
-                        if (near_ok && __activemask() == in_loop) mode = 1;
-                        else if (disk_ok && __activemask() == in_loop) mode = 2;
-                        if (mode == 0) break;
-                        const F2 ZH = rrtp::bc(C.h[mode]), ZHH = rrtp::bc(C.hh[mode]), ZH6 = rrtp::bc(C.h6[mode]);
+                        // the zone each ray is well inside of: 0 vacuum, 1 near the hole, 2 disk zone, -1 none (a parked half: vacuum)
+                        const int m0 = !alive[0] ? 0 : zone_for_burst(r0, fabsf(y0)), m1 = !alive[1] ? 0 : zone_for_burst(r1, fabsf(y1));
+                        const bool ok = it >= zburst_after && it + kBurst < max_steps && m0 >= 0 && m1 >= 0;
+                        if (!(ok && __activemask() == in_loop)) break;
+                        const F2 ZH = rrtp::pk(C.h[m0], C.h[m1]), ZHH = rrtp::pk(C.hh[m0], C.hh[m1]), ZH6 = rrtp::pk(C.h6[m0], C.h6[m1]);
                         const V3x2 Ps = P, Vs = V;
                         const F2 R2s = R2, Rs = R;
                         const unsigned c0s = em.count[0], c1s = em.count[1];
                         unsigned bd = 0, bu = 0;
-                        float mn = kInf, mx = 0.0f, my = 0.0f;
+                        float mn0 = kInf, mx0 = 0.0f, my0 = 0.0f, mn1 = kInf, mx1 = 0.0f, my1 = 0.0f;
 #pragma unroll 1
                         for (int kb = 0; kb < kBurst; ++kb) {
                             const V3x2 Q = P;
@@ -592,23 +598,22 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
                             rrtp::rk4_step2<SPIN>(C, P, V, ZH, ZHH, ZH6, R2, R, ma, mb);         // :64
                             R2 = rrtp::norm2_loop_2(P);
                             R = rrtp::sqrt2(R2);
-                            if (alive[0]) {
-                                mn = fminf(mn, fminf(q0, ma)); mx = fmaxf(mx, q0); my = fmaxf(my, yy0);
+                            mn0 = fminf(mn0, fminf(q0, ma)); mx0 = fmaxf(mx0, q0); my0 = fmaxf(my0, yy0);
+                            mn1 = fminf(mn1, fminf(q1, mb)); mx1 = fmaxf(mx1, q1); my1 = fmaxf(my1, yy1);
+                            if (alive[0] && q0 < zone_rmax) {
                                 const unsigned z = (yy0 < C.disk_zone_y && q0 < C.disk_zone_r && want_disk ? 1u : 0u) |
                                                    (yy0 < C.dust_zone_y && q0 < C.dust_zone_r && want_dust ? 2u : 0u);      // :57-58, :67
-                                if (z) { bd += z & 1u; bu += z >> 1; em.emit(0, rrtp::half_of(Q, 0), rrtp::half_of(V, 0), q0, mode, z); }
+                                if (z) { bd += z & 1u; bu += z >> 1; em.emit(0, rrtp::half_of(Q, 0), rrtp::half_of(V, 0), q0, m0, z); }
                             }
-                            if (alive[1]) {
-                                mn = fminf(mn, fminf(q1, mb)); mx = fmaxf(mx, q1); my = fmaxf(my, yy1);
+                            if (alive[1] && q1 < zone_rmax) {
                                 const unsigned z = (yy1 < C.disk_zone_y && q1 < C.disk_zone_r && want_disk ? 1u : 0u) |
                                                    (yy1 < C.dust_zone_y && q1 < C.dust_zone_r && want_dust ? 2u : 0u);
-                                if (z) { bd += z & 1u; bu += z >> 1; em.emit(1, rrtp::half_of(Q, 1), rrtp::half_of(V, 1), q1, mode, z); }
+                                if (z) { bd += z & 1u; bu += z >> 1; em.emit(1, rrtp::half_of(Q, 1), rrtp::half_of(V, 1), q1, m1, z); }
                             }
                         }
-                        // every pre-step state in the zone the step size came from (:56-62), above the horizon (:47) and in the
-                        // branch-free domain; `mn` also holds the stage radii
-                        const bool good = mode == 1 ? (mn >= zb_floor && mx < 18.0f)
-                                                    : (mn >= 18.0f && mx < C.disk_zone_r && my < C.disk_zone_y);
+                        // every pre-step state of a ray in the zone its step size came from (:56-62), above the horizon (:47), short
+                        // of the escape test (:120) and in the branch-free domain; `mn` also holds the stage radii
+                        const bool good = (!alive[0] || burst_was_valid(m0, mn0, mx0, my0)) && (!alive[1] || burst_was_valid(m1, mn1, mx1, my1));
                         if (good) { it += kBurst; n_disk += bd; n_dust += bu; continue; }
                         P = Ps; V = Vs; R2 = R2s; R = Rs;
                         em.count[0] = c0s; em.count[1] = c1s;
@@ -705,12 +710,8 @@ __global__ void __launch_bounds__(32, RRT_PACKED_MIN_BLOCKS) trace_kernel_p(cons
 #ifndef RRT_NO_ZONE_BURSTS
                         float y0, y1;
                         rrtp::upk(P.y, y0, y1);
-                        y0 = fabsf(y0); y1 = fabsf(y1);
-                        const bool can = it >= zburst_after && it + kBurst < max_steps;
-                        if (can && (!alive[0] || (r0 >= near_lo && r0 <= near_hi)) && (!alive[1] || (r1 >= near_lo && r1 <= near_hi)) &&
-                            __activemask() == in_loop) { rewind = true; break; }
-                        if (can && (!alive[0] || (r0 >= disk_lo && r0 <= disk_hi && y0 < disk_y)) &&
-                            (!alive[1] || (r1 >= disk_lo && r1 <= disk_hi && y1 < disk_y)) && __activemask() == in_loop) { rewind = true; break; }
+                        if (it >= zburst_after && it + kBurst < max_steps && (!alive[0] || zone_for_burst(r0, fabsf(y0)) >= 0) &&
+                            (!alive[1] || zone_for_burst(r1, fabsf(y1)) >= 0) && __activemask() == in_loop) { rewind = true; break; }
 #endif
                     }
 #endif
