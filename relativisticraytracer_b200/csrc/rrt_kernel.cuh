@@ -302,10 +302,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
     // the whole ray outside the fast domain (+inf: every step is redone)
     const float redo_below = fast_ok ? C.acc_rmin : __int_as_float(0x7f800000);
 #if RRT_BURST_K > 0
-    #ifndef RRT_BURST_UNROLL_EMIT
-#define RRT_BURST_UNROLL_EMIT RRT_BURST_UNROLL
-#endif
-    constexpr int kBurst = RRT_BURST_K, kBurstUnroll = MEDIA == kMediaInline ? RRT_BURST_UNROLL_MEDIA : (MEDIA == kMediaEmit ? RRT_BURST_UNROLL_EMIT : RRT_BURST_UNROLL);
+        constexpr int kBurst = RRT_BURST_K, kBurstUnroll = MEDIA == kMediaInline ? RRT_BURST_UNROLL_MEDIA : RRT_BURST_UNROLL;
     static_assert(kBurst % kBurstUnroll == 0, "burst length must be a multiple of its unroll factor");
     // every threshold a checked vacuum step compares a radius against from above: zones (:56-58), horizon (:47),
     // geodesics.h:33 through the redo guard
@@ -406,11 +403,7 @@ __device__ __forceinline__ void trace_ray(const FrameArgs& A, int x, int y, RayR
 #ifdef RRT_TWO_CHECKED   // A/B knob: keep the constant-step copy of the checked vacuum step in the media kernels too
             constexpr bool kOneCheckedStep = !RRT_FMAD;
 #else
-            #ifdef RRT_EMIT_ONE_CHECKED
-            constexpr bool kOneCheckedStep = !RRT_FMAD || (MEDIA != kMediaNone && RRT_BURST_K > 0);
-#else
-            constexpr bool kOneCheckedStep = !RRT_FMAD || (MEDIA == kMediaInline && RRT_BURST_K > 0);
-#endif
+                        constexpr bool kOneCheckedStep = !RRT_FMAD || (MEDIA == kMediaInline && RRT_BURST_K > 0);
 #endif
             if (kOneCheckedStep || r < zone_rmax) {
                 float h = C.h[0], h6 = C.h6[0];

@@ -182,9 +182,6 @@ __device__ __forceinline__ unsigned next_tile(const FrameArgs& A, const SplitArg
 #define RRT_STORE256 1   // a slot is one 32-byte sector: write it with ONE 256-bit store (sm_100: STG.256) instead of two halves
 #endif
 __device__ __forceinline__ void pool_put(uint4* slots, unsigned slot, uint4 a, uint4 b) {
-#if defined(RRT_DBG_EMIT) && RRT_DBG_EMIT == 4   // timing experiment only (wrong frames): every store of a warp hits the same row
-    slot = (blockIdx.x & 1023u) * 64u + (threadIdx.x & 31u);
-#endif
 #if RRT_STORE256
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(slots + 2ull * slot), "r"(a.x), "r"(a.y), "r"(a.z),
                  "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
@@ -327,11 +324,8 @@ __device__ __forceinline__ void redo_later(const SplitArgs& S, unsigned tile, in
 }
 
 // ---- pass kernel 1: trajectories ------------------------------------------------------------------------------------
-#ifndef RRT_MIN_BLOCKS_TRACE
-#define RRT_MIN_BLOCKS_TRACE RRT_MIN_BLOCKS
-#endif
 template <bool SPIN>
-__global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS_TRACE) trace_kernel(const __grid_constant__ FrameArgs A,
+__global__ void __launch_bounds__(kRenderBlock, RRT_MIN_BLOCKS) trace_kernel(const __grid_constant__ FrameArgs A,
                                                                               const __grid_constant__ SplitArgs S) {
     __shared__ unsigned chunk_tab[kRenderBlock / 32][kDescChunks];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
