@@ -8,39 +8,44 @@
 // frame on 8 GPUs (profiles/r2_tile_timeline_*.txt).
 //
 // What.  Per frame, on one stream, in passes that each fit the pool:
-//   trace_kernel   the same persistent one-warp tile loop and the same trace_ray as render_kernel, in kMediaEmit mode:
-//                  an in-zone step stores its sample (32 B: q, v, r, zones) instead of evaluating it.  A tile that
-//                  stored nothing is finished on the spot; otherwise its 32 exit states are stored too and the tile is
-//                  queued.  The longest chain is now the trajectory alone.
-//   media_kernel   evaluates the queued tiles' samples 32 at a time, every lane busy, with the SAME out-of-line functions
+//   trace_kernel_p the tracing loop of render_kernel_p (two rays per thread in packed f32x2 registers, FMAD contract; the
+//   / trace_kernel scalar trace_ray otherwise), in kMediaEmit mode: an in-zone step stores its sample (32 B: q, v, r, zones)
+//                  instead of evaluating it.  A ray that stored nothing is finished on the spot; a ray with samples leaves its
+//                  exit state behind them and its tile is queued.  The longest chain is now the trajectory alone.  With no
+//                  media code in the tracer the packed step pays off (the fused packed kernel lost its gain to per-half
+//                  media calls) and the burst idea extends into the step-size zones (zone bursts, trace_kernel_p).
+//   media_kernel   evaluates the queued tiles' samples 128 at a time, every lane busy, with the SAME out-of-line functions
 //                  the fused kernel calls (disk_density / dust_base / dust_strands / media_final), the expensive dust
 //                  strands compacted once more through shared memory, and overwrites each sample with (e.rgb, s).
-//   fold_kernel    one warp per queued tile: every lane folds its ray's samples in step order,
+//   fold_kernel    one warp per queued group of 32 rays: every lane folds its ray's samples in step order,
 //                  `I += e (1 - s) T; T *= s` with the fused kernel's own operations, then background, effects, store.
+//   sweep_kernel   the fused code for whatever the enqueued passes left (normally nothing).
 // Every ray is traced, sampled and folded by the same arithmetic in the same order as in render_kernel: frames, planes
 // and counters are bit-identical (tests/test_gpu_split.py).
 //
 // Pool layout (one pool per stream in flight, HBM; `slot` = 32 bytes, `row` = 32 slots, one per lane).
 //   A tracing warp owns a stream of rows, cut into chunks of `chunk_rows` rows which it takes from the pool with one
 //   atomic each (a chunk is used up by successive tiles; the next tile continues in the current chunk).  Lane l's k-th
-//   sample of a tile goes to slot l of the tile's k-th row -- so storing a sample needs NO communication between lanes and
-//   no allocation: a counter, an address, two 16-byte stores.  (The first form of this pipeline allocated a compacted
-//   record per step through a shared-memory cursor; that per-step critical section cost the trace kernel a 5-15 ms tail,
-//   tools/r2_gpu21.sh.)  Rows are as long as the tile's busiest lane needs; slots of lanes with fewer samples stay unused
-//   (never written, never read).  A lane that stored samples puts its ray's exit state behind its last one; a lane that
-//   stored none finishes its ray on the spot.
+//   sample of a tile goes to slot l of the tile's k-th row (row 2 k + hf for the two rays of a packed thread) -- so
+//   storing a sample needs NO communication between lanes and no allocation: a counter, an address, one 256-bit store.
+//   The chunks a tile can possibly reach are taken BEFORE it is traced (see Emitter: nothing atomic may sit in the ray
+//   loop; the first forms of this pipeline, which allocated per step or per chunk inside the loop, paid for it with a
+//   5-15 ms tail -- profiles/r2_split_history.md).  Rows are as long as the tile's busiest lane needs; slots of lanes with
+//   fewer samples stay unused (never written, never read).  A lane that stored samples puts its ray's exit state behind
+//   its last one; a lane that stored none finishes its ray on the spot.
 //   sample = {q.xyz, v.xyz, r, tag}, tag = zones | zone_index << 2;  after media_kernel the first 16 bytes are
 //            {e.r, e.g, e.b, s}, s = -1 for a sample that did not pass the 0.001 density gate (:71);
 //   state  = {p.xyz, v.xyz, steps | end << 28, 0}, stored by each lane behind its own last sample.
-//   A queued tile is described by a TileDesc (chunk bases, first row, samples per lane); media_kernel takes its work as
-//   (tile, first sample) items of kMediaBatch samples, so a disk-plane tile (64 000 samples) is spread over 500 warps.
-// A pass ends when the pool passes its high-water mark (the warps stop taking tiles); a tile that cannot get a chunk
-// gives up, is put on the pass's redo list and traced again by the next pass; whatever is left after the last pass
-// enqueued by the host is rendered by sweep_kernel (the fused code), so the frame is complete for any pool size.
+//   A queued group of 32 rays is described by a TileDesc (chunk bases, first row, row stride, samples per lane);
+//   media_kernel takes its work as (group, first sample) items of kMediaBatch samples, so a disk-plane tile (64 000 samples)
+//   is spread over 500 warps.
+// A pass ends when the pool is used up: a warp that cannot take its next tile's worst-case rows puts the tile on the pass's
+// redo list and stops; the next pass traces it.  Whatever is left after the last pass the host enqueued is rendered by
+// sweep_kernel, so the frame is complete for any pool size and any guess of the pass count.
 #pragma once
 
 namespace rrtk {
-constexpr int kDescChunks = 40;   // chunks one tile's rows can span: (max_steps + 2) / chunk_rows + 2 must fit
+constexpr int kDescChunks = 40;   // chunks one tile's rows can span: ((1 or 2) * (max_steps + 1) + 1) / chunk_rows + 2 must fit
 struct PassCtrl {
     unsigned cursor;          // slots handed out to warps so far (chunk granularity; may overshoot capacity)
     unsigned full;            // an allocation failed: stop taking tiles
@@ -65,7 +70,7 @@ struct WorkItem {
 struct SplitArgs {
     uint4* slots;             // 2 x uint4 per slot
     unsigned capacity;        // slots
-    unsigned high_water;      // stop taking tiles beyond this cursor
+    unsigned high_water;      // stop taking tiles beyond this cursor (unused since chunks are taken before a tile is traced: 2^32 - 1)
     unsigned chunk_rows;      // power of two
     unsigned chunk_shift;     // log2(chunk_rows)
     PassCtrl* pc;             // this pass
@@ -151,7 +156,7 @@ __device__ __forceinline__ unsigned num_tiles16(const FrameArgs& A) {
 }
 
 // Next tile of a pass (lane 0 decides, everyone gets it): the previous pass's redo list first, then fresh tickets.
-// `stop` makes a split pass end early (pool beyond its high-water mark).
+// `may_stop` lets a split pass end early (pool used up).
 __device__ __forceinline__ unsigned next_tile(const FrameArgs& A, const SplitArgs& S, unsigned ntiles, bool may_stop) {
     unsigned tile = kNone;
     if ((threadIdx.x & 31) == 0) {
