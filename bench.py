@@ -527,7 +527,7 @@ def main():
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                 tj = json.load(f)
             traffic = {"bytes": float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"]),
-                       "source": f"{tj['capture']} (dram__bytes_read.sum + dram__bytes_write.sum of one render_kernel launch, "
+                       "source": f"{tj['capture']} (dram__bytes_read.sum + dram__bytes_write.sum of one {tj.get('kernel', 'render_kernel')} launch, "
                                  f"ncu --set full, {tj['when']}); not measured by this run"}
         except (OSError, KeyError, ValueError):
             pass
